@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference's operator boundary for the PatchMatch hot path.
+
+`runcuda(gs)` here takes the same information the reference's `int runcuda(GlobalState &gs)`
+(gipuma.h:2) takes — AlgorithmParameters, the per-view Camera_cu fields, the view selection subset and
+the images — and produces the same outputs (`lines.norm4`: world normal + depth, `lines.c`: cost).  All
+compute goes through the C-ABI of `libgipuma_b200.so` (include/gipuma_b200.h, hand-written sm_100a
+CUDA); there is no CPU path: loading fails loudly when the library has not been built, and every call
+fails loudly without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgipuma_b200.so")
+
+GPM_RNG_REFERENCE, GPM_RNG_STATEFUL = 0, 1
+
+
+class GpmParams(C.Structure):
+    _fields_ = [("box_hsize", C.c_int), ("box_vsize", C.c_int),
+                ("tau_color", C.c_float), ("tau_gradient", C.c_float),
+                ("alpha", C.c_float), ("gamma", C.c_float),
+                ("min_disparity", C.c_float), ("max_disparity", C.c_float),
+                ("iterations", C.c_int), ("n_best", C.c_int), ("cost_comb", C.c_int),
+                ("good_factor", C.c_float), ("depthMin", C.c_float), ("depthMax", C.c_float)]
+
+
+class GpmCamera(C.Structure):
+    _fields_ = [("K", C.c_float * 9), ("K_inv", C.c_float * 9), ("R", C.c_float * 9),
+                ("M_inv", C.c_float * 9), ("R_orig_inv", C.c_float * 9),
+                ("t", C.c_float * 3), ("C", C.c_float * 3), ("P_col34", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("f", C.c_float), ("alpha", C.c_float),
+                ("baseline", C.c_float)]
+
+
+class GipumaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libgipuma_b200.so and declare the C-ABI.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GipumaError("%s is missing: build it with `python -m gipuma_b200.build` "
+                          "(no CPU fallback exists)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, fp = C.c_void_p, C.POINTER(C.c_float)
+    L.gpm_last_error.restype = C.c_char_p
+    L.gpm_version.restype = C.c_char_p
+    L.gpm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.gpm_destroy.argtypes = [vp]
+    L.gpm_destroy.restype = None
+    L.gpm_set_params.argtypes = [vp, C.POINTER(GpmParams)]
+    L.gpm_set_reference.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(GpmCamera)]
+    L.gpm_set_view.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.POINTER(GpmCamera)]
+    L.gpm_set_num_views.argtypes = [vp, C.c_int]
+    L.gpm_set_rng.argtypes = [vp, C.c_ulonglong, C.c_int]
+    L.gpm_set_state.argtypes = [vp, vp, vp, C.c_int]
+    L.gpm_get_state.argtypes = [vp, vp, vp, C.c_int]
+    L.gpm_init.argtypes = [vp]
+    L.gpm_sweep.argtypes = [vp, C.c_int]
+    L.gpm_phase.argtypes = [vp, C.c_int, C.c_int]
+    L.gpm_finalize.argtypes = [vp]
+    L.gpm_cost_eval.argtypes = [vp, vp, vp, C.c_int]
+    L.gpm_run.argtypes = [vp, fp]
+    L.gpm_get_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.gpm_reset_stats.argtypes = [vp]
+    L.gpm_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    L.gpm_stream.argtypes = [vp]
+    L.gpm_stream.restype = vp
+    for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_num_views",
+                 "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
+                 "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def pack_params(p) -> GpmParams:
+    return GpmParams(p.box_hsize, p.box_vsize, p.tau_color, p.tau_gradient, p.alpha, p.gamma,
+                     p.min_disparity, p.max_disparity, p.iterations, p.n_best, p.cost_comb,
+                     p.good_factor, p.depthMin, p.depthMax)
+
+
+def pack_camera(c) -> GpmCamera:
+    g = GpmCamera()
+    g.K[:] = c.K.ravel().tolist()
+    g.K_inv[:] = c.K_inv.ravel().tolist()
+    g.R[:] = c.R.ravel().tolist()
+    g.M_inv[:] = c.M_inv.ravel().tolist()
+    g.R_orig_inv[:] = c.R_orig_inv.ravel().tolist()
+    g.t[:] = c.t.ravel().tolist()
+    g.C[:] = c.C.ravel().tolist()
+    g.P_col34[:] = c.P[:, 3].ravel().tolist()
+    g.fx, g.fy, g.f, g.alpha, g.baseline = c.fx, c.fy, c.f, c.alpha, c.baseline
+    return g
+
+
+def _ptr(a):
+    """void* of a numpy array, a torch tensor (host or CUDA) or a raw integer address."""
+    if a is None:
+        return None, 0
+    if isinstance(a, int):
+        return C.c_void_p(a), 1
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data), 0
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr()), 1 if a.is_cuda else 0
+    raise TypeError("unsupported buffer type %r" % type(a))
+
+
+class Context:
+    """One gpm_ctx: a reference view with its source views on one GPU."""
+
+    def __init__(self, width: int, height: int, max_views: int, device: int = 0):
+        self.lib = load_library()
+        self.W, self.H, self.max_views, self.device = width, height, max_views, device
+        h = C.c_void_p()
+        self._check(self.lib.gpm_create(C.byref(h), device, width, height, max_views))
+        self.h = h
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GipumaError("gipuma_b200 error %d: %s" % (rc, self.lib.gpm_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- inputs ---------------------------------------------------------------------------------
+    def set_params(self, params):
+        p = pack_params(params)
+        self._check(self.lib.gpm_set_params(self.h, C.byref(p)))
+
+    def set_reference(self, img, cam, pitch_bytes: int = 0):
+        ptr, dev = _ptr(img)
+        g = pack_camera(cam)
+        self._check(self.lib.gpm_set_reference(self.h, ptr, pitch_bytes, dev, C.byref(g)))
+
+    def set_view(self, v: int, img, cam, pitch_bytes: int = 0):
+        ptr, dev = _ptr(img)
+        g = pack_camera(cam)
+        self._check(self.lib.gpm_set_view(self.h, v, ptr, pitch_bytes, dev, C.byref(g)))
+
+    def set_num_views(self, n: int):
+        self._check(self.lib.gpm_set_num_views(self.h, n))
+
+    def set_rng(self, seed: int, mode: int = GPM_RNG_REFERENCE):
+        self._check(self.lib.gpm_set_rng(self.h, seed, mode))
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.gpm_set_option(self.h, name.encode(), int(value)))
+
+    def load_scene(self, scene, seed: int = 0xC0FFEE, rng_mode: int = GPM_RNG_REFERENCE, images=None):
+        """Upload a gipuma_b200.scene.Scene (images may be overridden by a list of device tensors)."""
+        imgs = scene.images if images is None else images
+        self.set_params(scene.params)
+        self.set_reference(np.ascontiguousarray(imgs[0]) if isinstance(imgs, np.ndarray) else imgs[0], scene.cameras[0])
+        for v, idx in enumerate(scene.subset):
+            im = np.ascontiguousarray(imgs[idx]) if isinstance(imgs, np.ndarray) else imgs[idx]
+            self.set_view(v, im, scene.cameras[idx])
+        self.set_num_views(len(scene.subset))
+        self.set_rng(seed, rng_mode)
+
+    # -- state ----------------------------------------------------------------------------------
+    def set_state(self, norm4=None, cost=None):
+        """Overwrite the raw planes [H,W,4] and/or costs [H,W] (numpy or torch, host or device)."""
+        if isinstance(norm4, np.ndarray):
+            norm4 = np.ascontiguousarray(norm4, dtype=np.float32)
+        if isinstance(cost, np.ndarray):
+            cost = np.ascontiguousarray(cost, dtype=np.float32)
+        p4, d4 = _ptr(norm4)
+        pc, dc = _ptr(cost)
+        if norm4 is not None and cost is not None and d4 != dc:
+            raise ValueError("norm4 and cost must both be host or both be device buffers")
+        self._check(self.lib.gpm_set_state(self.h, p4, pc, max(d4, dc)))
+
+    def get_state(self):
+        n4 = np.empty((self.H, self.W, 4), dtype=np.float32)
+        c = np.empty((self.H, self.W), dtype=np.float32)
+        self._check(self.lib.gpm_get_state(self.h, C.c_void_p(n4.ctypes.data), C.c_void_p(c.ctypes.data), 0))
+        return n4, c
+
+    def get_state_into(self, norm4, cost):
+        """Copy the state into caller buffers (numpy or torch, host or device)."""
+        p4, d4 = _ptr(norm4)
+        pc, dc = _ptr(cost)
+        self._check(self.lib.gpm_get_state(self.h, p4, pc, max(d4, dc)))
+
+    # -- compute --------------------------------------------------------------------------------
+    def init(self):
+        self._check(self.lib.gpm_init(self.h))
+
+    def sweep(self, iterations: int):
+        self._check(self.lib.gpm_sweep(self.h, iterations))
+
+    def phase(self, colour: int, phase_mask: int):
+        self._check(self.lib.gpm_phase(self.h, colour, phase_mask))
+
+    def finalize(self):
+        self._check(self.lib.gpm_finalize(self.h))
+
+    def cost_eval(self, planes: np.ndarray) -> np.ndarray:
+        pl = np.ascontiguousarray(planes, dtype=np.float32)
+        out = np.empty((self.H, self.W), dtype=np.float32)
+        self._check(self.lib.gpm_cost_eval(self.h, C.c_void_p(pl.ctypes.data), C.c_void_p(out.ctypes.data), 0))
+        return out
+
+    def run(self) -> float:
+        """init + params.iterations sweeps + finalize; returns the sweep time in ms (reference's timed span)."""
+        ms = C.c_float(0)
+        self._check(self.lib.gpm_run(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def stats(self) -> dict:
+        s = (C.c_ulonglong * 8)()
+        self._check(self.lib.gpm_get_stats(self.h, s))
+        return {"launches": s[0], "hypotheses": s[1], "skipped": s[2], "pruned": s[3],
+                "pairs": s[4], "pairs_full": s[5]}
+
+    def reset_stats(self):
+        self._check(self.lib.gpm_reset_stats(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.gpm_stream(self.h) or 0)
+
+
+class LineState:
+    """Outputs in the reference's LineState layout (linestate.h:8-24)."""
+
+    def __init__(self, norm4: np.ndarray, c: np.ndarray):
+        self.norm4 = norm4          # [rows, cols, 4]: world normal xyz, depth (0 where cost == MAXCOST)
+        self.c = c                  # [rows, cols]
+
+
+def runcuda(scene, seed: int = 0xC0FFEE, rng_mode: int = GPM_RNG_REFERENCE, device: int = 0,
+            options: Optional[dict] = None):
+    """The reference's `runcuda(GlobalState&)` for a Scene: returns (LineState, sweep_ms, stats)."""
+    with Context(scene.cols, scene.rows, max(1, len(scene.subset)), device) as ctx:
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
+        ctx.load_scene(scene, seed=seed, rng_mode=rng_mode)
+        ms = ctx.run()
+        n4, c = ctx.get_state()
+        st = ctx.stats()
+    return LineState(n4, c), ms, st

@@ -1,0 +1,519 @@
+// gpm_api.cu — host side of libgipuma_b200.so: the C-ABI declared in include/gipuma_b200.h.
+// Replaces the host launcher gipuma<T>() (reference gipuma.cu:1825-1960) and, through the adapter in
+// runcuda_adapter.cu, int runcuda(GlobalState&) (gipuma.cu:1962-1970).
+//
+// Device memory layout (everything resident in HBM for the life of the context):
+//   planes   float4[H*W]   (n.xyz, d) row-major, stride W   — LineState::norm4 layout (linestate.h:10)
+//   cost     float [H*W]                                      — LineState::c
+//   refpad   float [(H+32) x pitch]  reference image, replicate-padded by 16 px, pitch multiple of 32 floats
+//   src      cudaArray (layered, R32F, W x H x max_views) + one texture object: Linear filter, the
+//            reference's addressing (Wrap + unnormalised, main.cpp:642-648), element read mode
+//   cams     ViewCam[max_views]  (K, R, t per source view) — copied to shared memory by every block
+//   rng      uint32[H*W*6]  XORWOW state per pixel (GPM_RNG_STATEFUL only)
+// No CPU fallback exists: every entry point needs a CUDA device and reports GPM_E_CUDA otherwise.
+#include "../../include/gipuma_b200.h"
+#include "gpm_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace gpm;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(GPM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+struct gpm_ctx {
+    int device = 0, W = 0, H = 0, maxV = 0, V = 0;
+    gpm_params prm{};
+    bool have_params = false, have_ref = false;
+    std::vector<char> have_view;
+    float4* planes = nullptr;
+    float* cost = nullptr;
+    unsigned* rng = nullptr;
+    float* refpad = nullptr;
+    int refpitch = 0;
+    float* staging = nullptr;        // W*H floats, upload scratch
+    cudaArray_t srcArr = nullptr;
+    cudaTextureObject_t srcTex = 0;
+    ViewCam* d_cams = nullptr;
+    std::vector<ViewCam> h_cams;
+    bool cams_dirty = true;
+    RefCam ref{};
+    unsigned long long seed = 0xC0FFEEULL;
+    int rng_mode = GPM_RNG_REFERENCE;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* d_stats = nullptr;
+    unsigned long long launches = 0;
+    int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
+    bool state_consistent = false;   // cost[] == cost(pixel, planes[]) through eval_plane for every pixel
+    int smem_optin = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
+{
+    if (!c->have_params) return fail(GPM_E_STATE, "gpm_set_params has not been called");
+    if (!c->have_ref) return fail(GPM_E_STATE, "gpm_set_reference has not been called");
+    if (c->V < 1) return fail(GPM_E_STATE, "no source views (gpm_set_num_views)");
+    for (int v = 0; v < c->V; v++)
+        if (!c->have_view[v]) return fail(GPM_E_STATE, "source view " + std::to_string(v) + " has not been set");
+    const gpm_params& p = c->prm;
+    memset(&P, 0, sizeof(P));
+    P.W = c->W;  P.H = c->H;  P.V = c->V;
+    const int box = p.box_hsize;
+    P.rad = init_phase ? box / 2 : (box - 1) / 2;          // gipuma.cu:1012 vs :1474
+    P.nside = P.rad + 1;                                    // i = -rad, -rad+2, ... <= rad
+    P.ns = P.nside * P.nside;
+    P.ns_pad = (P.ns + 3) & ~3;
+    P.halo = (box + 1) / 2;                                 // gipuma.cu:1844-1847
+    P.tile_w = GPM_TILE + 2 * P.halo;
+    int seg_cols = 32 / P.nside;                            // whole window columns per segment, <= 32 samples,
+    int want = (P.nside + 3) / 4;                           // aiming at >= 4 lower-bound checks per hypothesis
+    if (seg_cols > want) seg_cols = want;
+    if (seg_cols < 1) seg_cols = 1;
+    P.seg_len = seg_cols * P.nside;
+    if (P.seg_len > 32) P.seg_len = 32;
+    P.nseg = (P.ns + P.seg_len - 1) / P.seg_len;
+    P.refpitch = c->refpitch;
+    P.tau_color = p.tau_color;  P.tau_gradient = p.tau_gradient;  P.alpha = p.alpha;  P.gamma = p.gamma;
+    P.min_disp = p.min_disparity;  P.max_disp = p.max_disparity;
+    P.n_best = p.n_best;  P.cost_comb = p.cost_comb;  P.good_factor = p.good_factor;
+    P.prune = c->opt_prune;
+    P.dedupe_self = (c->opt_dedupe && (c->state_consistent || c->opt_trust_state)) ? 1 : 0;
+    P.dedupe_cand = c->opt_dedupe ? 1 : 0;
+    P.rng_mode = c->rng_mode;
+    P.ref = c->ref;
+    P.ref.depthMin = p.depthMin;  P.ref.depthMax = p.depthMax;
+    // warps per block: as many as fit (<= 16), leaving room for >= 2 resident blocks per SM
+    const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V) * sizeof(float);
+    const size_t fixed = ((size_t)P.tile_w * P.tile_w + (size_t)P.V * GPM_VIEWCAM_FLOATS + 4) * sizeof(float);
+    int nw = 16;
+    const size_t budget = 100 * 1024;
+    while (nw > 2 && fixed + nw * per_warp > budget) nw--;
+    if (c->opt_nwarps > 0) nw = c->opt_nwarps;
+    if (nw > 16) nw = 16;
+    P.nwarps = nw;
+    if (block_smem_bytes(P) > (size_t)c->smem_optin)
+        return fail(GPM_E_ARG, "configuration needs more shared memory per block than the device offers");
+    return GPM_OK;
+}
+
+int sync_cams(gpm_ctx* c)
+{
+    if (!c->cams_dirty) return GPM_OK;
+    CU(cudaMemcpyAsync(c->d_cams, c->h_cams.data(), sizeof(ViewCam) * c->maxV, cudaMemcpyHostToDevice, c->stream));
+    c->cams_dirty = false;
+    return GPM_OK;
+}
+
+int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
+{
+    const size_t smem = block_smem_bytes(P);
+    dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    k_sweep<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes, c->cost, c->rng,
+                                                      colour, mask, c->opt_stats ? c->d_stats : nullptr);
+    c->launches++;
+    CU(cudaGetLastError());
+    return GPM_OK;
+}
+
+int upload_image(gpm_ctx* c, const float* img, size_t pitch_bytes, int on_device, float** dev_img, size_t* dev_pitch_floats)
+{
+    if (pitch_bytes == 0) pitch_bytes = (size_t)c->W * sizeof(float);
+    if (pitch_bytes % sizeof(float)) return fail(GPM_E_ARG, "pitch_bytes must be a multiple of 4");
+    if (on_device) {
+        *dev_img = const_cast<float*>(img);
+        *dev_pitch_floats = pitch_bytes / sizeof(float);
+        return GPM_OK;
+    }
+    CU(cudaMemcpy2DAsync(c->staging, (size_t)c->W * sizeof(float), img, pitch_bytes, (size_t)c->W * sizeof(float), c->H,
+                         cudaMemcpyHostToDevice, c->stream));
+    *dev_img = c->staging;
+    *dev_pitch_floats = c->W;
+    return GPM_OK;
+}
+
+}  // namespace
+
+extern "C" const char* gpm_last_error(void) { return g_err.c_str(); }
+extern "C" const char* gpm_version(void) { return "gipuma_b200 0.1 (sm_100a)"; }
+
+extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int max_views)
+{
+    if (!out || width < 8 || height < 8 || max_views < 1 || max_views > GPM_MAX_VIEWS)
+        return fail(GPM_E_ARG, "gpm_create: bad arguments (max_views must be 1.." + std::to_string(GPM_MAX_VIEWS) + ")");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(GPM_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (gipuma_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(GPM_E_ARG, "gpm_create: no such device");
+    DeviceGuard g(device);
+    gpm_ctx* c = new gpm_ctx;
+    c->device = device;  c->W = width;  c->H = height;  c->maxV = max_views;
+    c->have_view.assign(max_views, 0);
+    c->h_cams.assign(max_views, ViewCam{});
+    const size_t n = (size_t)width * height;
+    c->refpitch = (width + 2 * GPM_APRON + 31) & ~31;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (err == cudaSuccess && r != cudaSuccess) err = r; return r == cudaSuccess; };
+    ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ok(cudaEventCreate(&c->ev0));
+    ok(cudaEventCreate(&c->ev1));
+    ok(cudaMalloc(&c->planes, n * sizeof(float4)));
+    ok(cudaMalloc(&c->cost, n * sizeof(float)));
+    ok(cudaMalloc(&c->staging, n * sizeof(float)));
+    ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
+    ok(cudaMalloc(&c->d_cams, sizeof(ViewCam) * max_views));
+    ok(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+    if (err == cudaSuccess) {
+        ok(cudaMemsetAsync(c->planes, 0, n * sizeof(float4), c->stream));      // LineState::resize zeroes (linestate.h:19-24)
+        ok(cudaMemsetAsync(c->cost, 0, n * sizeof(float), c->stream));
+        ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
+    }
+    if (err == cudaSuccess) {
+        cudaResourceDesc res;  memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;  res.res.array.array = c->srcArr;
+        cudaTextureDesc td;  memset(&td, 0, sizeof(td));
+        td.addressMode[0] = cudaAddressModeWrap;  td.addressMode[1] = cudaAddressModeWrap;   // main.cpp:644-645
+        td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
+        ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
+        ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        ok(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+    }
+    if (err != cudaSuccess) {
+        std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
+        gpm_destroy(c);
+        return fail(GPM_E_CUDA, m);
+    }
+    *out = c;
+    return GPM_OK;
+}
+
+extern "C" void gpm_destroy(gpm_ctx* c)
+{
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
+    if (c->srcArr) cudaFreeArray(c->srcArr);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->rng);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->d_cams);  cudaFree(c->d_stats);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int gpm_set_params(gpm_ctx* c, const gpm_params* p)
+{
+    if (!c || !p) return fail(GPM_E_ARG, "gpm_set_params: null argument");
+    if (p->box_hsize != p->box_vsize)
+        return fail(GPM_E_ARG, "box_hsize != box_vsize: the reference's tile loader (gipuma.cu:1517) is only defined for square windows");
+    if (p->box_hsize < 3 || p->box_hsize > GPM_MAX_BOX || !(p->box_hsize & 1))
+        return fail(GPM_E_ARG, "box size must be odd, 3.." + std::to_string(GPM_MAX_BOX));
+    if (p->cost_comb < 0 || p->cost_comb > 3) return fail(GPM_E_ARG, "cost_comb must be 0..3");
+    if (p->iterations < 0) return fail(GPM_E_ARG, "iterations must be >= 0");
+    c->prm = *p;
+    c->have_params = true;
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_num_views(gpm_ctx* c, int n)
+{
+    if (!c || n < 1 || n > c->maxV) return fail(GPM_E_ARG, "gpm_set_num_views: out of range");
+    c->V = n;
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_rng(gpm_ctx* c, unsigned long long seed, int mode)
+{
+    if (!c || (mode != GPM_RNG_REFERENCE && mode != GPM_RNG_STATEFUL)) return fail(GPM_E_ARG, "gpm_set_rng: bad mode");
+    DeviceGuard g(c->device);
+    c->seed = seed;
+    c->rng_mode = mode;
+    if (mode == GPM_RNG_STATEFUL && !c->rng) {
+        CU(cudaMalloc(&c->rng, (size_t)c->W * c->H * 6 * sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->rng, 0, (size_t)c->W * c->H * 6 * sizeof(unsigned), c->stream));
+    }
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_bytes, int on_device, const gpm_camera* cam)
+{
+    if (!c || !img || !cam) return fail(GPM_E_ARG, "gpm_set_reference: null argument");
+    DeviceGuard g(c->device);
+    float* d = nullptr;
+    size_t pf = 0;
+    int rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);
+    if (rc) return rc;
+    dim3 b(32, 8), gr((c->W + 2 * GPM_APRON + 31) / 32, (c->H + 2 * GPM_APRON + 7) / 8);
+    k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch);
+    CU(cudaGetLastError());
+    RefCam& r = c->ref;
+    memcpy(r.K_inv, cam->K_inv, sizeof(r.K_inv));
+    memcpy(r.M_inv, cam->M_inv, sizeof(r.M_inv));
+    memcpy(r.R_orig_inv, cam->R_orig_inv, sizeof(r.R_orig_inv));
+    memcpy(r.P34, cam->P_col34, sizeof(r.P34));
+    memcpy(r.C, cam->C, sizeof(r.C));
+    r.fx = cam->fx;  r.alpha = cam->alpha;  r.K2 = cam->K[2];  r.K5 = cam->K[5];
+    r.f = cam->f;  r.f_cam = cam->f;  r.baseline = cam->baseline;
+    c->have_ref = true;
+    c->state_consistent = false;
+    CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_bytes, int on_device, const gpm_camera* cam)
+{
+    if (!c || !img || !cam) return fail(GPM_E_ARG, "gpm_set_view: null argument");
+    if (v < 0 || v >= c->maxV) return fail(GPM_E_ARG, "gpm_set_view: view index out of range");
+    DeviceGuard g(c->device);
+    if (pitch_bytes == 0) pitch_bytes = (size_t)c->W * sizeof(float);
+    cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
+    m.srcPtr = make_cudaPitchedPtr(const_cast<float*>(img), pitch_bytes, c->W, c->H);
+    m.dstArray = c->srcArr;
+    m.dstPos = make_cudaPos(0, 0, v);
+    m.extent = make_cudaExtent(c->W, c->H, 1);
+    m.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpy3DAsync(&m, c->stream));
+    ViewCam& vc = c->h_cams[v];
+    memcpy(vc.K, cam->K, sizeof(vc.K));
+    memcpy(vc.R, cam->R, sizeof(vc.R));
+    memcpy(vc.t, cam->t, sizeof(vc.t));
+    c->cams_dirty = true;
+    c->have_view[v] = 1;
+    c->state_consistent = false;
+    if (!on_device) CU(cudaStreamSynchronize(c->stream));   // the caller may reuse its host buffer
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, int on_device)
+{
+    if (!c) return fail(GPM_E_ARG, "gpm_set_state: null context");
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)c->W * c->H;
+    const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (norm4) CU(cudaMemcpyAsync(c->planes, norm4, n * sizeof(float4), k, c->stream));
+    if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->state_consistent = false;
+    return GPM_OK;
+}
+
+extern "C" int gpm_get_state(gpm_ctx* c, float* norm4, float* cost, int on_device)
+{
+    if (!c) return fail(GPM_E_ARG, "gpm_get_state: null context");
+    DeviceGuard g(c->device);
+    const size_t n = (size_t)c->W * c->H;
+    const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (norm4) CU(cudaMemcpyAsync(norm4, c->planes, n * sizeof(float4), k, c->stream));
+    if (cost) CU(cudaMemcpyAsync(cost, c->cost, n * sizeof(float), k, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+static int do_init(gpm_ctx* c)
+{
+    KParams P;
+    int rc = build_kparams(c, true, P);
+    if (rc) return rc;
+    rc = sync_cams(c);
+    if (rc) return rc;
+    dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);                   // gipuma.cu:1870-1875
+    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr);
+    c->launches++;
+    CU(cudaGetLastError());
+    dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes,
+                                                                         c->cost, nullptr);
+    c->launches++;
+    CU(cudaGetLastError());
+    // init and sweeps use the same radius for odd boxes, so cost[] is consistent with planes[] afterwards
+    c->state_consistent = (c->prm.box_hsize / 2) == ((c->prm.box_hsize - 1) / 2);
+    return GPM_OK;
+}
+
+static int do_sweeps(gpm_ctx* c, int iterations)
+{
+    KParams P;
+    int rc = build_kparams(c, false, P);
+    if (rc) return rc;
+    rc = sync_cams(c);
+    if (rc) return rc;
+    for (int it = 0; it < iterations; it++) {                                  // gipuma.cu:1911-1941
+        rc = launch_colour(c, P, 0, 7);
+        if (rc) return rc;
+        rc = launch_colour(c, P, 1, 7);
+        if (rc) return rc;
+    }
+    return GPM_OK;
+}
+
+static int do_finalize(gpm_ctx* c)
+{
+    KParams P;
+    int rc = build_kparams(c, false, P);
+    if (rc) return rc;
+    dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
+    k_finalize<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost);
+    c->launches++;
+    CU(cudaGetLastError());
+    c->state_consistent = false;
+    return GPM_OK;
+}
+
+extern "C" int gpm_init(gpm_ctx* c)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    int rc = do_init(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_sweep(gpm_ctx* c, int iterations)
+{
+    if (!c || iterations < 0) return fail(GPM_E_ARG, "gpm_sweep: bad arguments");
+    DeviceGuard g(c->device);
+    int rc = do_sweeps(c, iterations);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_phase(gpm_ctx* c, int colour, int phase_mask)
+{
+    if (!c || colour < 0 || colour > 1 || phase_mask < 1 || phase_mask > 7) return fail(GPM_E_ARG, "gpm_phase: bad arguments");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = build_kparams(c, false, P);
+    if (rc) return rc;
+    rc = sync_cams(c);
+    if (rc) return rc;
+    rc = launch_colour(c, P, colour, phase_mask);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_finalize(gpm_ctx* c)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    int rc = do_finalize(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, int on_device)
+{
+    if (!c || !planes || !out_cost) return fail(GPM_E_ARG, "gpm_cost_eval: null argument");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = build_kparams(c, false, P);
+    if (rc) return rc;
+    rc = sync_cams(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->W * c->H;
+    float4* d_pl = nullptr;
+    float* d_out = nullptr;
+    if (on_device) { d_pl = (float4*)planes;  d_out = out_cost; }
+    else {
+        CU(cudaMalloc(&d_pl, n * sizeof(float4)));
+        CU(cudaMalloc(&d_out, n * sizeof(float)));
+        CU(cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    }
+    dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, d_pl, d_out, nullptr);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !on_device) e = cudaMemcpyAsync(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (!on_device) { cudaFree(d_pl);  cudaFree(d_out); }
+    if (e != cudaSuccess) return fail(GPM_E_CUDA, std::string("gpm_cost_eval: ") + cudaGetErrorString(e));
+    return GPM_OK;
+}
+
+extern "C" int gpm_run(gpm_ctx* c, float* sweep_ms)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    CU(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
+    c->launches = 0;
+    int rc = do_init(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev0, c->stream));                                    // gipuma.cu:1908
+    rc = do_sweeps(c, c->prm.iterations);
+    if (rc) return rc;
+    rc = do_finalize(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev1, c->stream));                                    // gipuma.cu:1946
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (sweep_ms) *sweep_ms = ms;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_get_stats(gpm_ctx* c, unsigned long long stats[8])
+{
+    if (!c || !stats) return fail(GPM_E_ARG, "gpm_get_stats: null argument");
+    DeviceGuard g(c->device);
+    CU(cudaMemcpyAsync(stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    stats[ST_LAUNCH] = c->launches;
+    return GPM_OK;
+}
+
+extern "C" int gpm_reset_stats(gpm_ctx* c)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    CU(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
+    c->launches = 0;
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
+{
+    if (!c || !name) return fail(GPM_E_ARG, "gpm_set_option: null argument");
+    const std::string n(name);
+    if (n == "prune") c->opt_prune = value != 0;
+    else if (n == "dedupe") c->opt_dedupe = value != 0;
+    else if (n == "trust_state") c->opt_trust_state = value != 0;
+    else if (n == "nwarps") c->opt_nwarps = value;
+    else if (n == "stats") c->opt_stats = value != 0;
+    else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
+    return GPM_OK;
+}
+
+extern "C" void* gpm_stream(gpm_ctx* c) { return c ? (void*)c->stream : nullptr; }

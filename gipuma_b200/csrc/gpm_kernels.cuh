@@ -1,0 +1,264 @@
+// gpm_kernels.cuh — __global__ kernels of the PatchMatch hot path (sm_100a).  See gpm_device.cuh.
+#pragma once
+#include "gpm_device.cuh"
+#include <curand_kernel.h>
+
+namespace gpm {
+
+// Stage the (32+2*halo)^2 reference window of tile (bx, by) and the per-view camera table in shared memory.
+// Unlike the reference's loader (gipuma.cu:1510-1525, skipped by threads that left early — SURVEY.md §7),
+// every thread takes part, so the whole window is always defined.
+__device__ __forceinline__ void stage_block(const KParams& P, const float* __restrict__ refpad,
+                                            const ViewCam* __restrict__ cams, float* tile, float* sCam,
+                                            int tile_x0, int tile_y0)
+{
+    const int tw = P.tile_w;
+    const float* src = refpad + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
+    for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
+        const int J = e / tw, I = e - J * tw;
+        tile[e] = src[(size_t)J * P.refpitch + I];
+    }
+    const float* c = reinterpret_cast<const float*>(cams);
+    for (int e = threadIdx.x; e < P.V * GPM_VIEWCAM_FLOATS; e += blockDim.x) sCam[e] = c[e];
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, const WarpStats& st, unsigned lane)
+{
+    if (lane == 0 && stats) {
+        atomicAdd(stats + ST_HYP, (unsigned long long)st.hyp);
+        atomicAdd(stats + ST_SKIP, (unsigned long long)st.skip);
+        atomicAdd(stats + ST_PRUNED, (unsigned long long)st.pruned);
+        atomicAdd(stats + ST_PAIRS, st.pairs);
+        atomicAdd(stats + ST_PAIRS_FULL, st.pairs_full);
+    }
+}
+
+// shared memory: [tile tw*tw][cams V*21][nwarps * warp_scratch][1 int work counter]
+__host__ __device__ inline size_t block_smem_bytes(const KParams& P)
+{
+    size_t fl = (size_t)P.tile_w * P.tile_w + (size_t)P.V * GPM_VIEWCAM_FLOATS +
+                (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V) + 4;
+    return fl * sizeof(float);
+}
+
+// ---- random plane initialisation — gipuma_init_cu2, gipuma.cu:996-1036 ----------------------
+__global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long long seed, float4* __restrict__ planes,
+                              unsigned* __restrict__ rng_state)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H) return;
+    curandState st;
+    curand_init(seed, y, x, &st);                                    // :1019 (reference seed: clock64())
+    Xorwow r;
+    r.v0 = st.v[0];  r.v1 = st.v[1];  r.v2 = st.v[2];  r.v3 = st.v[3];  r.v4 = st.v[4];  r.d = st.d;
+    const float px = __int2float_rn(x), py = __int2float_rn(y);
+    float vx, vy, vz;
+    view_vector(P.ref, px, py, vx, vy, vz);                         // :1025
+    // disp_now = curand_between(mind, maxd)                           :1028
+    const float disp = ffma(fsub(P.max_disp, P.min_disp), xorwow_uniform(r), P.min_disp);
+    // rndUnitVectorSphereMarsaglia_cu, :148-164
+    float a, b, sum;
+    do {
+        a = ffma(xorwow_uniform(r), 2.0f, -1.0f);
+        b = ffma(xorwow_uniform(r), 2.0f, -1.0f);
+        sum = ffma(a, a, fmul(b, b));
+    } while (sum >= 1.0f);
+    const float sq = fsqrt_(fsub(1.0f, sum));
+    float nx = fmul(fadd(a, a), sq), ny = fmul(fadd(b, b), sq), nz = fsub(1.0f, fadd(sum, sum));
+    if (dot3(nx, ny, nz, vx, vy, vz) > 0.0f) { nx = -nx;  ny = -ny;  nz = -nz; }   // vecOnHemisphere_cu :131-137
+    // depth = f * baseline / disp (:1031), d = getD_cu (:1034)
+    const float depth = fmul(fmul(P.ref.f_cam, P.ref.baseline), frcp(disp));
+    const float d = plane_d(P.ref, nx, ny, nz, px, py, depth);
+    planes[(size_t)y * P.W + x] = make_float4(nx, ny, nz, d);
+    if (rng_state) {
+        unsigned* o = rng_state + ((size_t)y * P.W + x) * 6;
+        o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
+    }
+}
+
+// ---- cost of the stored (or supplied) plane at every pixel — gipuma.cu:1040-1049 and gpm_cost_eval ----
+__global__ void __launch_bounds__(512)
+k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+            cudaTextureObject_t src, const float4* __restrict__ planes, float* __restrict__ cost,
+            unsigned long long* __restrict__ stats)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* sCam = tile + P.tile_w * P.tile_w;
+    float* scratch = sCam + P.V * GPM_VIEWCAM_FLOATS;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
+    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
+    __syncthreads();
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    WarpStats st = {0, 0, 0, 0, 0};
+    for (int idx = warp; idx < GPM_TILE * GPM_TILE; idx += P.nwarps) {
+        const int px = blockIdx.x * GPM_TILE + (idx & 31), py = blockIdx.y * GPM_TILE + (idx >> 5);
+        if (px >= P.W || py >= P.H) continue;
+        setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        const float4 n = planes[(size_t)py * P.W + px];
+        const float c = eval_plane(P, sCam, ws, src, n.x, n.y, n.z, n.w, __int_as_float(0x7f800000), lane, st);
+        if (lane == 0) cost[(size_t)py * P.W + px] = c;
+    }
+    flush_stats(stats, st, lane);
+}
+
+// ---- one checkerboard colour: close + far propagation + refinement, fused --------------------
+// gipuma_{black,red}_spatialPropClose_cu / spatialPropFar_cu / planeRefine_cu, gipuma.cu:1353-1823.
+// colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
+__global__ void __launch_bounds__(512)
+k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+        cudaTextureObject_t src, float4* __restrict__ planes, float* __restrict__ cost,
+        unsigned* __restrict__ rng_state, int colour, int phase_mask, unsigned long long* __restrict__ stats)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* sCam = tile + P.tile_w * P.tile_w;
+    float* scratch = sCam + P.V * GPM_VIEWCAM_FLOATS;
+    int* counter = reinterpret_cast<int*>(scratch + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V));
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
+    if (threadIdx.x == 0) *counter = P.nwarps;
+    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
+    __syncthreads();
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    const RefCam& cam = P.ref;
+    WarpStats st = {0, 0, 0, 0, 0};
+    const int W = P.W, H = P.H;
+
+    int idx = warp;                                                  // dynamic distribution of the tile's 512 pixels
+    while (idx < GPM_TILE * GPM_TILE / 2) {
+        // pixel of this colour — gipuma.cu:1730-1734 / 1786-1790
+        const int tx = idx & 31, ty = idx >> 5;
+        const int px = blockIdx.x * GPM_TILE + tx;
+        const int py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1);
+        if (px < W && py < H) {
+            const size_t center = (size_t)py * W + px;
+            setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+            const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
+            float4 norm_now = planes[center];
+            float cost_now = cost[center];
+            float disp_now = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);   // :1530
+
+            // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462)
+            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool mine_ok = false;
+            if (lane < 8) {
+                const int dist = lane < 4 ? 1 : 5;
+                const int dir = lane & 3;
+                const bool phase_on = (phase_mask >> (lane >> 2)) & 1;
+                int qx = px, qy = py;
+                bool ok;
+                if (dir == 0)      { ok = py > dist - 1;      qy = py - dist; }
+                else if (dir == 1) { ok = py < H - dist;      qy = py + dist; }
+                else if (dir == 2) { ok = px > dist - 1;      qx = px - dist; }
+                else               { ok = px < W - dist;      qx = px + dist; }
+                mine_ok = ok && phase_on;
+                if (mine_ok) mine = planes[(size_t)qy * W + qx];
+            }
+            const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
+            for (int k = 0; k < 8; k++) {
+                if (!((cand_mask >> k) & 1)) continue;
+                float4 nb;
+                nb.x = __shfl_sync(GPM_FULL, mine.x, k);  nb.y = __shfl_sync(GPM_FULL, mine.y, k);
+                nb.z = __shfl_sync(GPM_FULL, mine.z, k);  nb.w = __shfl_sync(GPM_FULL, mine.w, k);
+                // spatialPropagation_cu, gipuma.cu:832-874
+                const float disp_before = plane_depth(cam, nb.x, nb.y, nb.z, nb.w, fpx, fpy);
+                const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
+                // exact duplicates: cost(p, plane) is a pure function, so a plane equal to the current one or to an
+                // earlier candidate of this pixel cannot be accepted (`cost_before < *cost_now` is false)
+                const bool same_now = P.dedupe_self &&
+                                      __float_as_uint(nb.x) == __float_as_uint(norm_now.x) && __float_as_uint(nb.y) == __float_as_uint(norm_now.y) &&
+                                      __float_as_uint(nb.z) == __float_as_uint(norm_now.z) && __float_as_uint(nb.w) == __float_as_uint(norm_now.w);
+                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
+                                       __float_as_uint(nb.x) == __float_as_uint(mine.x) && __float_as_uint(nb.y) == __float_as_uint(mine.y) &&
+                                       __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
+                const bool dup = __any_sync(GPM_FULL, same_mine);
+                if (!in_range || same_now || dup) { st.skip++; continue; }
+                const float c = eval_plane(P, sCam, ws, src, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                if (c < cost_now) {                                                              // :867-871
+                    disp_now = disp_before;
+                    norm_now = nb;
+                    cost_now = c;
+                }
+            }
+
+            if (phase_mask & 4) {
+                // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
+                Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};       // GPM_RNG_REFERENCE: gs.cs is never written (gipuma.cu:1840,1608)
+                if (P.rng_mode == 1) {
+                    const unsigned* in = rng_state + center * 6;
+                    r.v0 = in[0];  r.v1 = in[1];  r.v2 = in[2];  r.v3 = in[3];  r.v4 = in[4];  r.d = in[5];
+                }
+                float vx, vy, vz;
+                view_vector(cam, fpx, fpy, vx, vy, vz);                                          // :948
+                const float fb = fmul(cam.baseline, cam.f);
+                float deltaN = 1.0f;
+                for (float deltaZ = fmul(P.max_disp, 0.5f); deltaZ >= 0.01f; deltaZ = fmul(deltaZ, 0.1f)) {   // :958-959
+                    const float rdisp = frcp(disp_now);                   // disp = f*baseline/depth (:904), kept fused
+                    const float hi = fmin_(ffma(rdisp, -fb, P.max_disp), deltaZ);        // maxDelta (:910)
+                    const float lo = fmin_(ffma(rdisp, fb, P.min_disp), deltaZ);         // -minDelta (:909)
+                    const float dz = ffma(xorwow_uniform(r), fadd(lo, hi), -lo);        // curand_between(minDelta, maxDelta) :914
+                    float dnew = ffma(rdisp, fb, dz);                                    // disp + deltaZ
+                    dnew = fmin_(P.max_disp, fmax_(P.min_disp, dnew));                   // :916
+                    const float depth_new = fmul(frcp(dnew), fb);                        // :918
+                    const float twoN = fadd(deltaN, deltaN);
+                    const float ax = fadd(norm_now.x, ffma(xorwow_uniform(r), twoN, -deltaN));   // :921-923
+                    const float ay = fadd(norm_now.y, ffma(twoN, xorwow_uniform(r), -deltaN));
+                    const float az = fadd(norm_now.z, ffma(twoN, xorwow_uniform(r), -deltaN));
+                    const float rs = frsq(ffma(az, az, ffma(ax, ax, fmul(ay, ay))));     // normalize_cu :113-120
+                    float4 cand;
+                    cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
+                    if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
+                    cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
+                    const float c = eval_plane(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    if (c < cost_now) {                                                          // :986-990 (no depth-range test)
+                        cost_now = c;
+                        disp_now = depth_new;
+                        norm_now = cand;
+                    }
+                    deltaN = fmul(deltaN, 0.25f);                                                // :992
+                }
+                if (P.rng_mode == 1 && lane == 0) {
+                    unsigned* o = rng_state + center * 6;
+                    o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
+                }
+            }
+            if (lane == 0) {                                                                     // :1585-1587
+                cost[center] = cost_now;
+                planes[center] = norm_now;
+            }
+        }
+        if (lane == 0) idx = atomicAdd(counter, 1);
+        idx = __shfl_sync(GPM_FULL, idx, 0);
+    }
+    flush_stats(stats, st, lane);
+}
+
+// ---- final depth / world normal — gipuma_compute_disp, gipuma.cu:1080-1103 ------------------
+__global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict__ planes, const float* __restrict__ cost)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H) return;
+    const size_t center = (size_t)y * P.W + x;
+    const float4 n = planes[center];
+    const float* R = P.ref.R_orig_inv;
+    float4 o;
+    o.x = ffma(n.z, R[2], ffma(n.x, R[0], fmul(n.y, R[1])));
+    o.y = ffma(n.z, R[5], ffma(n.x, R[3], fmul(n.y, R[4])));
+    o.z = ffma(n.z, R[8], ffma(n.x, R[6], fmul(n.y, R[7])));
+    o.w = (cost[center] != GPM_MAXCOST) ? plane_depth(P.ref, n.x, n.y, n.z, n.w, __int2float_rn(x), __int2float_rn(y)) : 0.0f;
+    planes[center] = o;
+}
+
+// replicate-pad the reference image by GPM_APRON on every side (== the texture's clamp addressing, main.cpp:644-645)
+__global__ void k_pad_reference(const float* __restrict__ img, size_t pitch_floats, int W, int H,
+                                float* __restrict__ out, int out_pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W + 2 * GPM_APRON || y >= H + 2 * GPM_APRON) return;
+    const int sx = min(max(x - GPM_APRON, 0), W - 1), sy = min(max(y - GPM_APRON, 0), H - 1);
+    out[(size_t)y * out_pitch + x] = img[(size_t)sy * pitch_floats + sx];
+}
+
+}  // namespace gpm

@@ -1,0 +1,139 @@
+/* gipuma_b200.h — C-ABI of the Blackwell-native PatchMatch hot path.
+ *
+ * This library replaces exactly one thing in kysucix/gipuma: the work behind
+ *      int runcuda(GlobalState &gs);                     (reference gipuma.h:2, gipuma.cu:1962-1970)
+ * i.e. gipuma<T>() (gipuma.cu:1825-1960): random plane initialisation, red/black checkerboard
+ * spatial propagation (close +-1 px, far +-5 px), plane refinement, the multi-view
+ * adaptive-support-weight photo-consistency cost, and the final depth / world-normal output.
+ *
+ * Plain C, no torch / CUDA types in the signatures: device pointers are passed as void* plus an
+ * `on_device` flag.  Every entry point returns 0 on success or a negative GPM_E_* code;
+ * gpm_last_error() returns a thread-local description.  One gpm_ctx per device / per reference view;
+ * contexts are independent (one per rank in multi-GPU runs).
+ *
+ * The runcuda() adapter that flattens the reference's managed GlobalState into these calls lives in
+ * gipuma_b200/csrc/runcuda_adapter.cu (it is the only code that knows GlobalState); see INTEGRATION.md.
+ */
+#ifndef GIPUMA_B200_H
+#define GIPUMA_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPM_MAX_VIEWS 64          /* source views per reference view (reference: costVector[32], gipuma.cu:736) */
+#define GPM_MAX_BOX   25          /* window size limit of the reference's tile loader (gipuma.cu:1513-1522) */
+
+enum {
+    GPM_OK = 0,
+    GPM_E_ARG = -1,               /* bad argument / unsupported parameter */
+    GPM_E_CUDA = -2,              /* a CUDA call failed; see gpm_last_error() */
+    GPM_E_STATE = -3              /* call sequence error (e.g. sweep before views are set) */
+};
+
+/* cost combination — algorithmparameters.h:17 */
+enum { GPM_COMB_ALL = 0, GPM_COMB_BEST_N = 1, GPM_COMB_ANGLE = 2, GPM_COMB_GOOD = 3 };
+
+/* RNG behaviour of the plane-refinement step.
+ * GPM_RNG_REFERENCE reproduces what the reference does: gs.cs is cudaMalloc'ed and never written
+ * (gipuma.cu:1840, 1608, 1702), so every refinement kernel starts each pixel from an all-zero XORWOW
+ * state.  GPM_RNG_STATEFUL keeps a per-pixel XORWOW state seeded at init and advanced by every draw
+ * (what the code evidently intended); it has no reference output to compare against. */
+enum { GPM_RNG_REFERENCE = 0, GPM_RNG_STATEFUL = 1 };
+
+/* The AlgorithmParameters fields the device path reads (algorithmparameters.h:53-84). */
+typedef struct gpm_params {
+    int   box_hsize, box_vsize;         /* odd, equal, <= GPM_MAX_BOX */
+    float tau_color, tau_gradient;
+    float alpha, gamma;
+    float min_disparity, max_disparity; /* = f*baseline/depthMax, f*baseline/depthMin (main.cpp:905-906) */
+    int   iterations;
+    int   n_best;
+    int   cost_comb;                    /* GPM_COMB_* */
+    float good_factor;
+    float depthMin, depthMax;           /* cameras[REFERENCE].depthMin/Max (main.cpp:898-903) */
+} gpm_params;
+
+/* The Camera_cu fields the device path reads (camera.h:7-62), 3x3 matrices row-major. */
+typedef struct gpm_camera {
+    float K[9], K_inv[9], R[9], M_inv[9], R_orig_inv[9];
+    float t[3], C[3], P_col34[3];
+    float fx, fy, f, alpha, baseline;
+} gpm_camera;
+
+typedef struct gpm_ctx gpm_ctx;
+
+/* Create a context on CUDA device `device` for width x height images and up to `max_views`
+ * source views.  Replaces the allocations of gipuma<T>() (gipuma.cu:1840) and main.cpp:927-933. */
+int gpm_create(gpm_ctx** out, int device, int width, int height, int max_views);
+void gpm_destroy(gpm_ctx* ctx);
+
+int gpm_set_params(gpm_ctx* ctx, const gpm_params* p);
+
+/* Reference image + camera (index REFERENCE=0 of gs.imgs / gs.cameras->cameras, config.h:21).
+ * `img` is row-major float, `pitch_bytes` between rows; host or device memory. */
+int gpm_set_reference(gpm_ctx* ctx, const float* img, size_t pitch_bytes, int on_device, const gpm_camera* cam);
+
+/* Source view `v` (0-based position in viewSelectionSubset, main.cpp:888-892). */
+int gpm_set_view(gpm_ctx* ctx, int v, const float* img, size_t pitch_bytes, int on_device, const gpm_camera* cam);
+
+/* Number of source views actually used (viewSelectionSubsetNumber, main.cpp:918). */
+int gpm_set_num_views(gpm_ctx* ctx, int n_views);
+
+/* Seed of the per-pixel curand_init(seed, y, x) at initialisation (gipuma.cu:1019; the reference uses
+ * clock64()) and the refinement RNG mode. */
+int gpm_set_rng(gpm_ctx* ctx, unsigned long long seed, int mode);
+
+/* Overwrite / read the raw per-pixel state: planes [height*width] float4 (n.xyz in the reference
+ * camera frame, w = plane distance d) and costs [height*width] float, both row-major with stride =
+ * width — the LineState layout (linestate.h:8-24).  Either pointer may be NULL. */
+int gpm_set_state(gpm_ctx* ctx, const float* norm4, const float* cost, int on_device);
+int gpm_get_state(gpm_ctx* ctx, float* norm4, float* cost, int on_device);
+
+/* gipuma_init_cu2 (gipuma.cu:996-1051): random plane + initial cost for every pixel. */
+int gpm_init(gpm_ctx* ctx);
+
+/* `iterations` red/black sweeps (gipuma.cu:1911-1941).  One iteration = black{close,far,refine} then
+ * red{close,far,refine}; the three phases of a colour are fused into one launch. */
+int gpm_sweep(gpm_ctx* ctx, int iterations);
+
+/* One phase of one colour, for step-level parity tests: colour 0 = black, 1 = red;
+ * phase_mask bit0 = close (gipuma.cu:1471-1588), bit1 = far (:1353-1468), bit2 = refine (:1590-1711). */
+int gpm_phase(gpm_ctx* ctx, int colour, int phase_mask);
+
+/* gipuma_compute_disp (gipuma.cu:1080-1103): normals to world frame, w <- depth (0 where cost == MAXCOST). */
+int gpm_finalize(gpm_ctx* ctx);
+
+/* Multi-view cost of caller-supplied planes at every pixel (no accept logic) — pmCostMultiview_cu
+ * (gipuma.cu:720-806) through the iteration-time path; `planes`/`out_cost` like gpm_set_state. */
+int gpm_cost_eval(gpm_ctx* ctx, const float* planes, float* out_cost, int on_device);
+
+/* Whole job as runcuda() does it: init, params.iterations sweeps, finalize; results are left in the
+ * context (gpm_get_state).  `sweep_ms` (may be NULL) receives the CUDA-event time from the first sweep
+ * kernel to the end of the final kernel — the reference's own timed span (gipuma.cu:1908-1952). */
+int gpm_run(gpm_ctx* ctx, float* sweep_ms);
+
+/* Counters of the last gpm_sweep/gpm_run: [0] kernels launched, [1] hypotheses offered,
+ * [2] hypotheses skipped as exact duplicates / out of depth range, [3] hypotheses cut short by the
+ * exact lower bound, [4] (view,sample) evaluations done, [5] (view,sample) evaluations a full run would do. */
+int gpm_get_stats(gpm_ctx* ctx, unsigned long long stats[8]);
+int gpm_reset_stats(gpm_ctx* ctx);
+
+/* Tuning / diagnostics; results are bit-identical for every setting.
+ * "prune" (1): exact lower-bound early-out; "dedupe" (1): skip bit-identical candidate planes;
+ * "trust_state" (0): treat a state loaded with gpm_set_state as cost-consistent; "nwarps" (0 = auto): warps per block;
+ * "stats" (1): maintain the gpm_get_stats counters. */
+int gpm_set_option(gpm_ctx* ctx, const char* name, int value);
+
+/* The CUDA stream all work of this context is enqueued on (as a void*), for event timing by callers. */
+void* gpm_stream(gpm_ctx* ctx);
+
+const char* gpm_last_error(void);
+const char* gpm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIPUMA_B200_H */
