@@ -44,6 +44,7 @@ struct gpm_ctx {
     float4* planes = nullptr;
     float* cost = nullptr;
     unsigned* rng = nullptr;
+    unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
     int refpitch = 0;
     float* staging = nullptr;        // W*H floats, upload scratch
@@ -60,7 +61,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    bool state_consistent = false;   // cost[] == cost(pixel, planes[]) through eval_plane for every pixel
+    int opt_cost_variant = 1;
     int smem_optin = 0;
 };
 
@@ -89,26 +90,37 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.ns_pad = (P.ns + 3) & ~3;
     P.halo = (box + 1) / 2;                                 // gipuma.cu:1844-1847
     P.tile_w = GPM_TILE + 2 * P.halo;
-    int seg_cols = 32 / P.nside;                            // whole window columns per segment, <= 32 samples,
-    int want = (P.nside + 3) / 4;                           // aiming at >= 4 lower-bound checks per hypothesis
-    if (seg_cols > want) seg_cols = want;
-    if (seg_cols < 1) seg_cols = 1;
-    P.seg_len = seg_cols * P.nside;
-    if (P.seg_len > 32) P.seg_len = 32;
-    P.nseg = (P.ns + P.seg_len - 1) / P.seg_len;
+    // rounds of whole window columns: 1, 1, 2, 4, ... columns, at most 32 samples per round
+    {
+        int cols_done = 0, r = 0, want = 1;
+        const int max_cols = (32 / P.nside) > 0 ? (32 / P.nside) : 1;
+        while (cols_done < P.nside && r < 16) {
+            int cols = want < max_cols ? want : max_cols;
+            if (r == 15 || cols > P.nside - cols_done) cols = P.nside - cols_done;
+            cols_done += cols;
+            int end = cols_done * P.nside;
+            if (end > 255) return fail(GPM_E_ARG, "window too large");
+            P.round_end[r++] = (unsigned char)end;
+            if (r >= 2) want *= 2;
+        }
+        P.nrounds = r;
+        if (!c->opt_prune || init_phase) { P.nrounds = 0; int e = 0;      // no pruning: fewest rounds of <= 32 samples
+            while (e < P.ns) { e += max_cols * P.nside; if (e > P.ns) e = P.ns; P.round_end[P.nrounds++] = (unsigned char)e; } }
+    }
     P.refpitch = c->refpitch;
     P.tau_color = p.tau_color;  P.tau_gradient = p.tau_gradient;  P.alpha = p.alpha;  P.gamma = p.gamma;
     P.min_disp = p.min_disparity;  P.max_disp = p.max_disparity;
     P.n_best = p.n_best;  P.cost_comb = p.cost_comb;  P.good_factor = p.good_factor;
     P.prune = c->opt_prune;
-    P.dedupe_self = (c->opt_dedupe && (c->state_consistent || c->opt_trust_state)) ? 1 : 0;
+    P.dedupe_self = c->opt_dedupe ? 1 : 0;
+    P.cost_variant = init_phase ? 0 : c->opt_cost_variant;
     P.dedupe_cand = c->opt_dedupe ? 1 : 0;
     P.rng_mode = c->rng_mode;
     P.ref = c->ref;
     P.ref.depthMin = p.depthMin;  P.ref.depthMax = p.depthMax;
     // warps per block: as many as fit (<= 16), leaving room for >= 2 resident blocks per SM
     const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V) * sizeof(float);
-    const size_t fixed = ((size_t)P.tile_w * P.tile_w + (size_t)P.V * GPM_VIEWCAM_FLOATS + 4) * sizeof(float);
+    const size_t fixed = ((size_t)fixed_smem_floats(P) + 4) * sizeof(float);
     int nw = 16;
     const size_t budget = 100 * 1024;
     while (nw > 2 && fixed + nw * per_warp > budget) nw--;
@@ -133,7 +145,7 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
     const size_t smem = block_smem_bytes(P);
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
     k_sweep<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes, c->cost, c->rng,
-                                                      colour, mask, c->opt_stats ? c->d_stats : nullptr);
+                                                      c->prov, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
     return GPM_OK;
@@ -183,6 +195,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaEventCreate(&c->ev1));
     ok(cudaMalloc(&c->planes, n * sizeof(float4)));
     ok(cudaMalloc(&c->cost, n * sizeof(float)));
+    ok(cudaMalloc(&c->prov, n));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
     ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
     ok(cudaMalloc(&c->d_cams, sizeof(ViewCam) * max_views));
@@ -190,6 +203,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     if (err == cudaSuccess) {
         ok(cudaMemsetAsync(c->planes, 0, n * sizeof(float4), c->stream));      // LineState::resize zeroes (linestate.h:19-24)
         ok(cudaMemsetAsync(c->cost, 0, n * sizeof(float), c->stream));
+        ok(cudaMemsetAsync(c->prov, 2, n, c->stream));
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
@@ -222,7 +236,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
-    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->rng);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->rng);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -284,7 +298,7 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     r.fx = cam->fx;  r.alpha = cam->alpha;  r.K2 = cam->K[2];  r.K5 = cam->K[5];
     r.f = cam->f;  r.f_cam = cam->f;  r.baseline = cam->baseline;
     c->have_ref = true;
-    c->state_consistent = false;
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
     CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
     return GPM_OK;
 }
@@ -308,7 +322,7 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     memcpy(vc.t, cam->t, sizeof(vc.t));
     c->cams_dirty = true;
     c->have_view[v] = 1;
-    c->state_consistent = false;
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
     if (!on_device) CU(cudaStreamSynchronize(c->stream));   // the caller may reuse its host buffer
     return GPM_OK;
 }
@@ -321,8 +335,10 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (norm4) CU(cudaMemcpyAsync(c->planes, norm4, n * sizeof(float4), k, c->stream));
     if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
+    // provenance of the supplied costs is unknown (2) unless the caller vouches that they came from an
+    // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
+    CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? 0 : 2, n, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->state_consistent = false;
     return GPM_OK;
 }
 
@@ -354,8 +370,7 @@ static int do_init(gpm_ctx* c)
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
-    // init and sweeps use the same radius for odd boxes, so cost[] is consistent with planes[] afterwards
-    c->state_consistent = (c->prm.box_hsize / 2) == ((c->prm.box_hsize - 1) / 2);
+    CU(cudaMemsetAsync(c->prov, 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation
     return GPM_OK;
 }
 
@@ -384,7 +399,7 @@ static int do_finalize(gpm_ctx* c)
     k_finalize<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost);
     c->launches++;
     CU(cudaGetLastError());
-    c->state_consistent = false;
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));   // planes are world-frame outputs now
     return GPM_OK;
 }
 
@@ -512,6 +527,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "trust_state") c->opt_trust_state = value != 0;
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
+    else if (n == "cost_variant") c->opt_cost_variant = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;
 }

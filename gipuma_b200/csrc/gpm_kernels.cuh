@@ -33,11 +33,11 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const War
     }
 }
 
-// shared memory: [tile tw*tw][cams V*21][nwarps * warp_scratch][1 int work counter]
+// shared memory: [tile tw*tw][cams V*21][pad to 16 B][nwarps * warp_scratch][1 int work counter]
+__host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (P.tile_w * P.tile_w + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
 __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
 {
-    size_t fl = (size_t)P.tile_w * P.tile_w + (size_t)P.V * GPM_VIEWCAM_FLOATS +
-                (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V) + 4;
+    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V) + 4;
     return fl * sizeof(float);
 }
 
@@ -85,7 +85,7 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float* sCam = tile + P.tile_w * P.tile_w;
-    float* scratch = sCam + P.V * GPM_VIEWCAM_FLOATS;
+    float* scratch = smem + fixed_smem_floats(P);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
@@ -97,7 +97,9 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
         if (px >= P.W || py >= P.H) continue;
         setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
-        const float c = eval_plane(P, sCam, ws, src, n.x, n.y, n.z, n.w, __int_as_float(0x7f800000), lane, st);
+        const float inf = __int_as_float(0x7f800000);
+        const float c = P.cost_variant ? eval_plane<true>(P, sCam, ws, src, n.x, n.y, n.z, n.w, inf, lane, st)
+                                       : eval_plane<false>(P, sCam, ws, src, n.x, n.y, n.z, n.w, inf, lane, st);
         if (lane == 0) cost[(size_t)py * P.W + px] = c;
     }
     flush_stats(stats, st, lane);
@@ -109,12 +111,13 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 __global__ void __launch_bounds__(512)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, float4* __restrict__ planes, float* __restrict__ cost,
-        unsigned* __restrict__ rng_state, int colour, int phase_mask, unsigned long long* __restrict__ stats)
+        unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, int colour, int phase_mask,
+        unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
     float* sCam = tile + P.tile_w * P.tile_w;
-    float* scratch = sCam + P.V * GPM_VIEWCAM_FLOATS;
+    float* scratch = smem + fixed_smem_floats(P);
     int* counter = reinterpret_cast<int*>(scratch + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V));
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
@@ -139,6 +142,8 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             float4 norm_now = planes[center];
             float cost_now = cost[center];
             float disp_now = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);   // :1530
+            // which rounding variant of the cost function produced cost_now: 0 = init/refine, 1 = propagation, 2 = unknown
+            int prov_now = prov[center];
 
             // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462)
             float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -167,7 +172,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
                 // exact duplicates: cost(p, plane) is a pure function, so a plane equal to the current one or to an
                 // earlier candidate of this pixel cannot be accepted (`cost_before < *cost_now` is false)
-                const bool same_now = P.dedupe_self &&
+                const bool same_now = P.dedupe_self && prov_now == 1 &&
                                       __float_as_uint(nb.x) == __float_as_uint(norm_now.x) && __float_as_uint(nb.y) == __float_as_uint(norm_now.y) &&
                                       __float_as_uint(nb.z) == __float_as_uint(norm_now.z) && __float_as_uint(nb.w) == __float_as_uint(norm_now.w);
                 const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
@@ -175,11 +180,12 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
-                const float c = eval_plane(P, sCam, ws, src, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                const float c = eval_plane<true>(P, sCam, ws, src, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
                     norm_now = nb;
                     cost_now = c;
+                    prov_now = 1;
                 }
             }
 
@@ -211,8 +217,9 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
                     if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
                     cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
-                    const float c = eval_plane(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    const float c = eval_plane<false>(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
                     if (c < cost_now) {                                                          // :986-990 (no depth-range test)
+                        prov_now = 0;
                         cost_now = c;
                         disp_now = depth_new;
                         norm_now = cand;
@@ -227,6 +234,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             if (lane == 0) {                                                                     // :1585-1587
                 cost[center] = cost_now;
                 planes[center] = norm_now;
+                prov[center] = (unsigned char)prov_now;
             }
         }
         if (lane == 0) idx = atomicAdd(counter, 1);

@@ -47,11 +47,11 @@ def make_case(name):
     if name == "small":
         return S.make_config(1)
     if name == "v10":
-        return S.make_config(2, rows=360, cols=480)
+        return S.make_config(2, rows=352, cols=480)
     if name == "b25":
-        return S.make_config(3, rows=240, cols=320, n_views=30)
+        return S.make_config(3, rows=256, cols=320, n_views=30)
     if name == "v47":
-        return S.make_config(4, rows=240, cols=320)
+        return S.make_config(4, rows=256, cols=320)
     if name == "cfg2":
         return S.make_config(2)
     if name == "cfg3":
