@@ -16,7 +16,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgipuma_b200.so")
+LIB_PATH = os.environ.get("GIPUMA_B200_LIB", os.path.join(_HERE, "libgipuma_b200.so"))
 
 GPM_RNG_REFERENCE, GPM_RNG_STATEFUL = 0, 1
 

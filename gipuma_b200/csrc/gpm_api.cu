@@ -90,22 +90,18 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.ns_pad = (P.ns + 3) & ~3;
     P.halo = (box + 1) / 2;                                 // gipuma.cu:1844-1847
     P.tile_w = GPM_TILE + 2 * P.halo;
-    // rounds of whole window columns: 1, 1, 2, 4, ... columns, at most 32 samples per round
+    // rounds of 32 consecutive samples (one per lane); the remainder forms a last, shorter round.  A window with
+    // fewer than 48 samples (b <= 11) is split into two equal rounds instead.
     {
-        int cols_done = 0, r = 0, want = 1;
-        const int max_cols = (32 / P.nside) > 0 ? (32 / P.nside) : 1;
-        while (cols_done < P.nside && r < 16) {
-            int cols = want < max_cols ? want : max_cols;
-            if (r == 15 || cols > P.nside - cols_done) cols = P.nside - cols_done;
-            cols_done += cols;
-            int end = cols_done * P.nside;
-            if (end > 255) return fail(GPM_E_ARG, "window too large");
-            P.round_end[r++] = (unsigned char)end;
-            if (r >= 2) want *= 2;
+        int r = 0;
+        if (P.ns > 32 && P.ns < 48) {
+            P.round_end[r++] = (unsigned char)((P.ns + 1) / 2);
+            P.round_end[r++] = (unsigned char)P.ns;
+        } else {
+            for (int e = 32; e < P.ns && r < 15; e += 32) P.round_end[r++] = (unsigned char)e;
+            P.round_end[r++] = (unsigned char)P.ns;
         }
         P.nrounds = r;
-        if (!c->opt_prune || init_phase) { P.nrounds = 0; int e = 0;      // no pruning: fewest rounds of <= 32 samples
-            while (e < P.ns) { e += max_cols * P.nside; if (e > P.ns) e = P.ns; P.round_end[P.nrounds++] = (unsigned char)e; } }
     }
     P.refpitch = c->refpitch;
     P.tau_color = p.tau_color;  P.tau_gradient = p.tau_gradient;  P.alpha = p.alpha;  P.gamma = p.gamma;
@@ -121,11 +117,11 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     // warps per block: as many as fit (<= 16), leaving room for >= 2 resident blocks per SM
     const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V) * sizeof(float);
     const size_t fixed = ((size_t)fixed_smem_floats(P) + 4) * sizeof(float);
-    int nw = 16;
+    int nw = GPM_LB_THREADS / 32;
     const size_t budget = 100 * 1024;
     while (nw > 2 && fixed + nw * per_warp > budget) nw--;
     if (c->opt_nwarps > 0) nw = c->opt_nwarps;
-    if (nw > 16) nw = 16;
+    if (nw > GPM_LB_THREADS / 32) nw = GPM_LB_THREADS / 32;
     P.nwarps = nw;
     if (block_smem_bytes(P) > (size_t)c->smem_optin)
         return fail(GPM_E_ARG, "configuration needs more shared memory per block than the device offers");

@@ -77,7 +77,11 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
 }
 
 // ---- cost of the stored (or supplied) plane at every pixel — gipuma.cu:1040-1049 and gpm_cost_eval ----
-__global__ void __launch_bounds__(512)
+#ifndef GPM_LB_THREADS
+#define GPM_LB_THREADS 512       // max threads per block of the warp-per-pixel kernels (16 warps)
+#define GPM_LB_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
             cudaTextureObject_t src, const float4* __restrict__ planes, float* __restrict__ cost,
             unsigned long long* __restrict__ stats)
@@ -108,7 +112,7 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 // ---- one checkerboard colour: close + far propagation + refinement, fused --------------------
 // gipuma_{black,red}_spatialPropClose_cu / spatialPropFar_cu / planeRefine_cu, gipuma.cu:1353-1823.
 // colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, float4* __restrict__ planes, float* __restrict__ cost,
         unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, int colour, int phase_mask,
