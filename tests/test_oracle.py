@@ -1,0 +1,117 @@
+"""The CPU oracle (oracle/gipuma_oracle.c) checked on its own and against golden outputs of the compiled reference.
+The oracle cannot be bit-exact with the GPU (fast-math intrinsics, texture hardware): tolerances are stated here."""
+import numpy as np
+import pytest
+
+from conftest import golden_names
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    from gipuma_b200 import scene as S
+    return S.make_config(1, rows=48, cols=64)
+
+
+def test_texture_model_basics(small_scene):
+    from oracle import pyoracle
+    o = pyoracle.Oracle(small_scene)
+    img = small_scene.images[1]
+    H, W = img.shape
+    assert o.tex2d(img, 10 + 0.5, 7 + 0.5) == img[7, 10]                          # texel centres are exact
+    assert o.tex2d(img, 10 + 1.0, 7 + 0.5) == pytest.approx(0.5 * (img[7, 10] + img[7, 11]))
+    assert o.tex2d(img, -5.0, 3.5) == img[3, 0] and o.tex2d(img, W + 9.0, H + 2.0) == img[H - 1, W - 1]   # clamp
+    # weights have 8 fractional bits: moving by less than 1/512 texel does not change the sample
+    assert o.tex2d(img, 20.5 + 0.25, 9.5) == o.tex2d(img, 20.5 + 0.25 + 1.0 / 1024, 9.5)
+
+
+def test_plane_depth_roundtrip(small_scene):
+    import ctypes as C
+    from oracle import pyoracle
+    o = pyoracle.Oracle(small_scene)
+    o.lib.gpo_plane_d.restype = C.c_float
+    o.lib.gpo_plane_depth.restype = C.c_float
+    fp = C.POINTER(C.c_float)
+    o.lib.gpo_plane_d.argtypes = [C.c_void_p, fp, C.c_int, C.c_int, C.c_float]
+    o.lib.gpo_plane_depth.argtypes = [C.c_void_p, fp, C.c_int, C.c_int]
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        n = rng.normal(size=3)
+        n[2] = -abs(n[2]) - 0.5
+        n = (n / np.linalg.norm(n)).astype(np.float32)
+        px, py, depth = int(rng.integers(0, 64)), int(rng.integers(0, 48)), float(rng.uniform(300, 800))
+        n4 = np.zeros(4, np.float32)
+        n4[:3] = n
+        n4[3] = o.lib.gpo_plane_d(C.byref(o.ref), n4.ctypes.data_as(fp), px, py, depth)
+        back = o.lib.gpo_plane_depth(C.byref(o.ref), n4.ctypes.data_as(fp), px, py)
+        assert back == pytest.approx(depth, rel=2e-4)          # getD_cu (gipuma.cu:96-111) inverts getDepthFromPlane3_cu (:694-705)
+
+
+def test_zero_state_xorwow_stream():
+    """Pin P2: an all-zero XORWOW state returns 362437*k (curand_kernel.h), so curand_uniform is ~8.4e-5 * k."""
+    import ctypes as C
+    from oracle import pyoracle
+    from gipuma_b200 import scene as S
+    sc = S.make_config(1, rows=48, cols=64)
+    o = pyoracle.Oracle(sc)
+    # gpo_random_plane with the zero state: first uniform = 362437 * 2^-32 + 2^-33
+    pl = o.random_plane(5, 5, [0, 0, 0, 0, 0, 0])
+    assert np.isfinite(pl).all() and abs(np.linalg.norm(pl[:3]) - 1) < 1e-5
+
+
+def test_true_surface_has_lower_cost_than_wrong_depth(small_scene):
+    from oracle import pyoracle
+    sc = small_scene
+    o = pyoracle.Oracle(sc)
+    pl = np.zeros((sc.rows, sc.cols, 4), np.float32)
+    pl[..., 2] = -1
+    pl[..., 3] = sc.gt_depth                       # fronto-parallel plane through the true depth (ref camera = K[I|0])
+    good = o.cost_eval(pl)
+    pl[..., 3] = sc.gt_depth * 1.08
+    bad = o.cost_eval(pl)
+    inner = (slice(10, -10), slice(10, -10))
+    assert good[inner].mean() < 0.7 * bad[inner].mean()
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_cost_matches_compiled_reference(golden, name):
+    """Pins the C restatement to the compiled reference: same planes, cost within 2e-3 relative (fast-math
+    intrinsics and the texture unit's arithmetic are the only differences), on a bounded band of rows."""
+    from oracle import pyoracle
+    sc, z = golden[name]
+    o = pyoracle.Oracle(sc)
+    y0, y1 = 16, 16 + max(4, 2048 // (sc.n_views * sc.cols // 8 + 1))
+    y1 = min(y1, sc.rows - 8)
+    c = o.cost_eval(z["init_norm4"], y0, y1)
+    ref = z["init_planes_sweep_cost"]
+    err = np.abs(c[y0:y1] - ref[y0:y1]) / np.maximum(1.0, ref[y0:y1])
+    assert np.percentile(err, 99) < 2e-3 and err.max() < 5e-2
+    ci = o.cost_eval(z["init_norm4"], y0, y1, init_radius=True)
+    erri = np.abs(ci[y0:y1] - z["init_cost"][y0:y1]) / np.maximum(1.0, z["init_cost"][y0:y1])
+    assert np.percentile(erri, 99) < 2e-3
+
+
+def test_oracle_black_sweep_agrees_with_reference_decisions(golden):
+    """Accept decisions are an argmin, so a CPU restatement flips near-ties: require >= 97 % of the updated pixels
+    to carry exactly the plane the compiled reference chose (bit pattern of a COPIED neighbour plane) on a row band."""
+    from oracle import pyoracle
+    if not golden_names():
+        pytest.skip("no golden fixtures")
+    name = golden_names()[0]
+    sc, z = golden[name]
+    o = pyoracle.Oracle(sc)
+    y0, y1 = 16, 40
+    pl, c = o.phase(z["init_norm4"], z["init_cost"], 0, 3, y0, y1)       # close + far propagation of the black pixels
+    ref4 = z["black_norm4"]
+    ys, xs = np.mgrid[y0:y1, 0:sc.cols]
+    black = ((xs + ys) & 1) == 0
+    # reference state after close+far+refine: a refined pixel differs from any copied plane; compare only pixels
+    # whose reference plane is still one of the initial planes (i.e. no refinement accepted)
+    init = z["init_norm4"]
+    same_as_some_initial = np.zeros(black.shape, bool)
+    for dy, dx in [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1), (-5, 0), (5, 0), (0, -5), (0, 5)]:
+        yy = np.clip(ys + dy, 0, sc.rows - 1)
+        xx = np.clip(xs + dx, 0, sc.cols - 1)
+        same_as_some_initial |= np.all(ref4[ys, xs] == init[yy, xx], axis=-1)
+    sel = black & same_as_some_initial
+    agree = np.all(pl[ys, xs][sel] == ref4[ys, xs][sel], axis=-1)
+    assert sel.sum() > 50 and agree.mean() > 0.97
