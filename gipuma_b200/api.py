@@ -77,10 +77,17 @@ def load_library():
     L.gpm_reset_stats.argtypes = [vp]
     L.gpm_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.gpm_stream.argtypes = [vp]
+    L.gpm_init_planes.argtypes = [vp]
+    L.gpm_shard_num_stages.argtypes = [vp]
+    L.gpm_shard_stage_floats.argtypes = [vp, C.c_int]
+    L.gpm_shard_stage_floats.restype = C.c_longlong
+    L.gpm_shard_eval.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.gpm_shard_accept.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.gpm_stream.restype = vp
     for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_num_views",
                  "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
-                 "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option"):
+                 "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option",
+                 "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_eval", "gpm_shard_accept"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -234,6 +241,28 @@ class Context:
         ms = C.c_float(0)
         self._check(self.lib.gpm_run(self.h, C.byref(ms)))
         return float(ms.value)
+
+    # -- source-view sharding (multi-GPU) -----------------------------------------------------------
+    def init_planes(self):
+        self._check(self.lib.gpm_init_planes(self.h))
+
+    def shard_num_stages(self) -> int:
+        n = self.lib.gpm_shard_num_stages(self.h)
+        if n < 0:
+            self._check(n)
+        return n
+
+    def shard_stage_floats(self, stage: int) -> int:
+        n = self.lib.gpm_shard_stage_floats(self.h, stage)
+        if n < 0:
+            self._check(int(n))
+        return int(n)
+
+    def shard_eval(self, colour: int, stage: int, xchg):
+        self._check(self.lib.gpm_shard_eval(self.h, colour, stage, C.c_void_p(xchg.data_ptr())))
+
+    def shard_accept(self, colour: int, stage: int, gathered, world: int):
+        self._check(self.lib.gpm_shard_accept(self.h, colour, stage, C.c_void_p(gathered.data_ptr()), world))
 
     def stats(self) -> dict:
         s = (C.c_ulonglong * 8)()

@@ -44,6 +44,9 @@ struct gpm_ctx {
     float4* planes = nullptr;
     float* cost = nullptr;
     unsigned* rng = nullptr;
+    float* dispbuf = nullptr;        // view-shard mode: disp_now carried between the stages of one colour
+    float4* candbuf = nullptr;       // view-shard mode: refinement candidate of the current step
+    float* canddepth = nullptr;
     unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
     int refpitch = 0;
@@ -215,6 +218,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         ok(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
     }
     if (err != cudaSuccess) {
         std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
@@ -232,7 +236,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
-    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->rng);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -491,6 +495,95 @@ extern "C" int gpm_run(gpm_ctx* c, float* sweep_ms)
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     if (sweep_ms) *sweep_ms = ms;
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+
+// ---- source-view sharding (multi-GPU) -------------------------------------------------------------------------
+static int shard_refine_steps(const gpm_params& p)
+{
+    int n = 0;
+    for (float dz = p.max_disparity * 0.5f; dz >= 0.01f; dz = dz * 0.1f) n++;      // gipuma.cu:958-959
+    return n;
+}
+
+extern "C" int gpm_shard_num_stages(gpm_ctx* c)
+{
+    if (!c || !c->have_params) { fail(GPM_E_STATE, "gpm_shard_num_stages: parameters not set");  return -1; }
+    return 2 + shard_refine_steps(c->prm);
+}
+
+extern "C" long long gpm_shard_stage_floats(gpm_ctx* c, int stage)
+{
+    if (!c || !c->have_params || stage < 0) { fail(GPM_E_ARG, "gpm_shard_stage_floats: bad arguments");  return -1; }
+    const long long half = (long long)c->H * ((c->W + 1) / 2);
+    const int slots = stage == 1 ? 8 : 1;
+    return (stage == 0 ? 2 : 1) * half * slots * c->prm.n_best;
+}
+
+static int shard_common(gpm_ctx* c, int stage, KParams& P)
+{
+    if (c->prm.cost_comb != GPM_COMB_BEST_N) return fail(GPM_E_ARG, "view sharding supports cost_comb = best_n only");
+    if (c->prm.n_best < 1 || c->prm.n_best > 32) return fail(GPM_E_ARG, "view sharding needs 1 <= n_best <= 32");
+    if (stage < 0 || stage >= 2 + shard_refine_steps(c->prm)) return fail(GPM_E_ARG, "no such stage");
+    int rc = build_kparams(c, stage == 0, P);
+    if (rc) return rc;
+    rc = sync_cams(c);
+    if (rc) return rc;
+    if (!c->dispbuf) {
+        const size_t n = (size_t)c->W * c->H;
+        CU(cudaMalloc(&c->dispbuf, n * sizeof(float)));
+        CU(cudaMalloc(&c->candbuf, n * sizeof(float4)));
+        CU(cudaMalloc(&c->canddepth, n * sizeof(float)));
+    }
+    return GPM_OK;
+}
+
+extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev)
+{
+    if (!c || !xchg_dev || colour < 0 || colour > 1) return fail(GPM_E_ARG, "gpm_shard_eval: bad arguments");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = shard_common(c, stage, P);
+    if (rc) return rc;
+    dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    k_shard_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes, c->cost,
+                                                                          c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage, xchg_dev);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));       // the caller's collective runs on another stream
+    return GPM_OK;
+}
+
+extern "C" int gpm_shard_accept(gpm_ctx* c, int colour, int stage, const float* gathered_dev, int world)
+{
+    if (!c || !gathered_dev || colour < 0 || colour > 1 || world < 1 || world > 8) return fail(GPM_E_ARG, "gpm_shard_accept: bad arguments");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = shard_common(c, stage, P);
+    if (rc) return rc;
+    dim3 b(32, 8), gr(((P.W + 1) / 2 + 31) / 32, (P.H + 7) / 8);
+    k_shard_accept<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost, c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage,
+                                            gathered_dev, world);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+// random planes only (stage 0 of the sharded flow computes the initial cost over all ranks' views)
+extern "C" int gpm_init_planes(gpm_ctx* c)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = build_kparams(c, true, P);
+    if (rc) return rc;
+    dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
+    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr);
+    c->launches++;
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }

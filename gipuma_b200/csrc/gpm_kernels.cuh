@@ -247,6 +247,196 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
     flush_stats(stats, st, lane);
 }
 
+// ============================================================================================================
+// Source-view sharding across GPUs (BASELINE config 4).  Every rank holds the full plane/cost state
+// and a SUBSET of the source views.  Per-view costs are independent (gipuma.cu:742-778); only the combination needs
+// all views.  For COMB_BEST_N the n_best smallest costs over all views are the n_best smallest of the union of every
+// rank's n_best smallest, so each rank exports, per pixel and hypothesis slot, its ascending local top-n_best
+// (k_shard_eval), the lists are all-gathered over NCCL, and every rank merges them, sums in ascending order — the
+// reference's order (gipuma.cu:779-797) — and applies the accept logic redundantly (k_shard_accept).  All ranks
+// therefore keep bit-identical state, identical to a single-GPU run over all views.
+//   stage 0        initial cost of the stored planes        (1 slot,  radius box/2)
+//   stage 1        close + far propagation candidates       (8 slots)
+//   stage 2 + s    refinement step s                         (1 slot; sequential: step s+1 depends on step s' accept)
+// Exchange index of pixel (x, y): y * ceil(W/2) + x/2 (pixels of one colour have distinct x/2 within a row).
+// ============================================================================================================
+__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
+k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+             cudaTextureObject_t src, const float4* __restrict__ planes, const float* __restrict__ cost,
+             const unsigned char* __restrict__ prov, float* __restrict__ dispbuf, float4* __restrict__ candbuf,
+             float* __restrict__ canddepth, int colour, int stage, float* __restrict__ xchg)
+{
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float* sCam = tile + P.tile_w * P.tile_w;
+    float* scratch = smem + fixed_smem_floats(P);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
+    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
+    __syncthreads();
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    const RefCam& cam = P.ref;
+    WarpStats st = {0, 0, 0, 0, 0};
+    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
+    const int slots = (stage == 1) ? 8 : 1;
+    const float inf = __int_as_float(0x7f800000);
+    // stage 0 visits every pixel (both colours, like gipuma_init_cu2); the others one colour
+    const int npix = (stage == 0) ? GPM_TILE * GPM_TILE : GPM_TILE * GPM_TILE / 2;
+    for (int idx = warp; idx < npix; idx += P.nwarps) {
+        int px, py;
+        if (stage == 0) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
+        else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }
+        if (px >= W || py >= H) continue;
+        const size_t center = (size_t)py * W + px;
+        // stage 0 exchanges both colours: two half-resolution planes back to back
+        float* out = xchg + (((stage == 0 ? (size_t)((px + py) & 1) * H * Wh : 0) + (size_t)py * Wh + (px >> 1)) * slots) * nb;
+        setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
+        const float4 norm_now = planes[center];
+        float c0, c1;
+        if (stage == 0) {
+            eval_plane<false>(P, sCam, ws, src, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
+            local_topn(P, c0, c1, lane, out);
+        } else if (stage == 1) {
+            const int prov_now = prov[center];
+            if (lane == 0) dispbuf[center] = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
+            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool mine_ok = false;
+            if (lane < 8) {
+                const int dist = lane < 4 ? 1 : 5, dir = lane & 3;
+                int qx = px, qy = py;
+                bool ok;
+                if (dir == 0)      { ok = py > dist - 1;  qy = py - dist; }
+                else if (dir == 1) { ok = py < H - dist;  qy = py + dist; }
+                else if (dir == 2) { ok = px > dist - 1;  qx = px - dist; }
+                else               { ok = px < W - dist;  qx = px + dist; }
+                mine_ok = ok;
+                if (mine_ok) mine = planes[(size_t)qy * W + qx];
+            }
+            const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
+            for (int k = 0; k < 8; k++) {
+                float4 nbp;
+                nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
+                nbp.z = __shfl_sync(GPM_FULL, mine.z, k);  nbp.w = __shfl_sync(GPM_FULL, mine.w, k);
+                bool skip = !((cand_mask >> k) & 1);
+                if (!skip) {
+                    const float d = plane_depth(cam, nbp.x, nbp.y, nbp.z, nbp.w, fpx, fpy);
+                    const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
+                    // self-dedupe is only neutral against the cost at kernel entry if no earlier slot is accepted; the
+                    // accept kernel cannot know, so only the candidate-vs-candidate rule is used here
+                    const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
+                                           __float_as_uint(nbp.x) == __float_as_uint(mine.x) && __float_as_uint(nbp.y) == __float_as_uint(mine.y) &&
+                                           __float_as_uint(nbp.z) == __float_as_uint(mine.z) && __float_as_uint(nbp.w) == __float_as_uint(mine.w);
+                    skip = !in_range || __any_sync(GPM_FULL, same_mine);
+                    (void)prov_now;
+                }
+                if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
+                eval_plane<true>(P, sCam, ws, src, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+                local_topn(P, c0, c1, lane, out + k * nb);
+            }
+        } else {
+            // refinement step s = stage - 2: getRndDispAndUnitVector_cu with the zero-state stream advanced by 4*s draws
+            const int sidx = stage - 2;
+            Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};
+            float deltaZ = fmul(P.max_disp, 0.5f), deltaN = 1.0f;
+            for (int i = 0; i < sidx; i++) { for (int j = 0; j < 4; j++) xorwow_next(r);  deltaZ = fmul(deltaZ, 0.1f);  deltaN = fmul(deltaN, 0.25f); }
+            const float disp_now = dispbuf[center];
+            float vx, vy, vz;
+            view_vector(cam, fpx, fpy, vx, vy, vz);
+            const float fb = fmul(cam.baseline, cam.f);
+            const float rdisp = frcp(disp_now);
+            const float hi = fmin_(ffma(rdisp, -fb, P.max_disp), deltaZ);
+            const float lo = fmin_(ffma(rdisp, fb, P.min_disp), deltaZ);
+            const float dz = ffma(xorwow_uniform(r), fadd(lo, hi), -lo);
+            float dnew = ffma(rdisp, fb, dz);
+            dnew = fmin_(P.max_disp, fmax_(P.min_disp, dnew));
+            const float depth_new = fmul(frcp(dnew), fb);
+            const float twoN = fadd(deltaN, deltaN);
+            const float ax = fadd(norm_now.x, ffma(xorwow_uniform(r), twoN, -deltaN));
+            const float ay = fadd(norm_now.y, ffma(twoN, xorwow_uniform(r), -deltaN));
+            const float az = fadd(norm_now.z, ffma(twoN, xorwow_uniform(r), -deltaN));
+            const float rs = frsq(ffma(az, az, ffma(ax, ax, fmul(ay, ay))));
+            float4 cand;
+            cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
+            if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
+            cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
+            if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
+            eval_plane<false>(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            local_topn(P, c0, c1, lane, out);
+        }
+    }
+}
+
+// merged cost of one slot: the n_best smallest over all ranks' lists, summed ascending, / count  (gipuma.cu:779-803)
+__device__ __forceinline__ float shard_merge(const float* __restrict__ g, size_t rank_stride, int world, int nb)
+{
+    int pos[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float sum = 0.0f;
+    int taken = 0;
+    for (int i = 0; i < nb; i++) {
+        float best = __int_as_float(0x7f800000);
+        int br = -1;
+        for (int r = 0; r < world; r++) {
+            if (pos[r] < nb) { const float v = g[r * rank_stride + pos[r]]; if (v < best) { best = v;  br = r; } }
+        }
+        if (br < 0 || !(best < GPM_MAXCOST)) break;        // only views with c < MAXCOST count (numValidViews)
+        pos[br]++;
+        sum = fadd(sum, best);
+        taken++;
+    }
+    float cost = fmul(frcp(__int2float_rn(taken)), sum);
+    if (taken < 1) cost = GPM_MAXCOST;
+    if (cost != cost || cost > GPM_MAXCOST || cost < 0.0f) cost = GPM_MAXCOST;
+    return cost;
+}
+
+__global__ void k_shard_accept(const __grid_constant__ KParams P, float4* __restrict__ planes, float* __restrict__ cost,
+                               unsigned char* __restrict__ prov, float* __restrict__ dispbuf,
+                               const float4* __restrict__ candbuf, const float* __restrict__ canddepth,
+                               int colour, int stage, const float* __restrict__ gathered, int world)
+{
+    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
+    const int hx = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (hx >= Wh || py >= H) return;
+    const int ncol = (stage == 0) ? 2 : 1;
+    for (int cc = 0; cc < ncol; cc++) {
+        const int col = (stage == 0) ? cc : colour;
+        const int px = 2 * hx + ((py + col) & 1);                      // the pixel of this colour with x/2 == hx in row py
+        if (px >= W) continue;
+        const size_t center = (size_t)py * W + px;
+        const int slots = (stage == 1) ? 8 : 1;
+        const size_t per_rank = (size_t)ncol * H * Wh * slots * nb;
+        const float* g = gathered + (((stage == 0 ? (size_t)col * H * Wh : 0) + (size_t)py * Wh + hx) * slots) * nb;
+        if (stage == 0) {
+            cost[center] = shard_merge(g, per_rank, world, nb);
+            prov[center] = 0;
+        } else if (stage == 1) {
+            float4 norm_now = planes[center];
+            float cost_now = cost[center];
+            float disp_now = dispbuf[center];
+            int prov_now = prov[center];
+            const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
+            for (int k = 0; k < 8; k++) {
+                const float c = shard_merge(g + k * nb, per_rank, world, nb);
+                if (c < cost_now) {
+                    const int dist = k < 4 ? 1 : 5, dir = k & 3;
+                    const int qx = px + (dir == 2 ? -dist : dir == 3 ? dist : 0), qy = py + (dir == 0 ? -dist : dir == 1 ? dist : 0);
+                    norm_now = planes[(size_t)qy * W + qx];                 // other colour: not written by this launch
+                    disp_now = plane_depth(P.ref, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
+                    cost_now = c;
+                    prov_now = 1;
+                }
+            }
+            planes[center] = norm_now;  cost[center] = cost_now;  dispbuf[center] = disp_now;  prov[center] = (unsigned char)prov_now;
+        } else {
+            const float c = shard_merge(g, per_rank, world, nb);
+            if (c < cost[center]) {
+                cost[center] = c;  planes[center] = candbuf[center];  dispbuf[center] = canddepth[center];  prov[center] = 0;
+            }
+        }
+    }
+}
+
 // ---- final depth / world normal — gipuma_compute_disp, gipuma.cu:1080-1103 ------------------
 __global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict__ planes, const float* __restrict__ cost)
 {

@@ -1,0 +1,163 @@
+"""Multi-GPU drivers for the PatchMatch hot path: one process per GPU, `torch.distributed` for the plumbing.
+
+Two axes shard; the reference itself is single-GPU (main.cpp:658-692).
+
+1. **Reference-view batch** — independent units.  The reference runs one process per reference image
+   (scripts/dtu_fast.sh:30-55); `assign_reference_views` deals reference views round-robin to ranks and
+   `run_reference_view_batch` runs each on the rank's own context.  No data-path collective; `bench.py --gpus N` is
+   this mode (weak scaling).
+
+2. **Source-view shard** inside one reference view (BASELINE config 4: 47 views over 4 GPUs).  Per-view costs are
+   independent; only their combination needs all views (gipuma.cu:742-806).  `north_star` words this as "allreduce
+   of best cost/plane", which is NOT the reference's rule (best-n over ALL views, summed in ascending order); the
+   exact formulation used here: per stage, every rank exports per pixel and hypothesis slot its ascending n_best
+   smallest per-view costs (gpm_shard_eval), the lists are all-gathered (`dist.all_gather_into_tensor`, NCCL over
+   NVLink), and every rank merges, combines and applies the accept logic redundantly (gpm_shard_accept).  State
+   stays bit-identical on all ranks and identical to a single-GPU run.  Collectives per iteration:
+   2 colours x (1 propagation + S refinement steps) = 8 on DTU parameters; payload per rank and colour:
+   H*ceil(W/2)*8*n_best*4 B for propagation (7.4 MB at 640x480, n_best 3), 1/8 of that per refinement step.
+   The exchange is a genuine step of the algorithm (a hypothesis can only be accepted once all views are known), so
+   it cannot be fused away; it is tiny next to the sampling work.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+MAXCOST = 1000.0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# partitioning (pure host logic)
+# ----------------------------------------------------------------------------------------------------------------
+
+def assign_reference_views(n_reference_views: int, rank: int, world: int) -> List[int]:
+    """Reference views r, r+world, ... for `rank` (the shell loop of scripts/dtu_fast.sh:30-55, dealt round-robin)."""
+    return list(range(rank, n_reference_views, world))
+
+
+def partition_views(n_views: int, world: int) -> List[List[int]]:
+    """Positions 0..n_views-1 of viewSelectionSubset split into `world` contiguous, balanced shards."""
+    base, extra = divmod(n_views, world)
+    out, start = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        out.append(list(range(start, start + n)))
+        start += n
+    return out
+
+
+def local_topn(costs: np.ndarray, n_best: int) -> np.ndarray:
+    """Ascending n_best smallest of the per-view costs along the last axis, padded with +inf; costs >= MAXCOST are
+    clamped to MAXCOST first (gipuma.cu:771-774).  NumPy mirror of the device function `local_topn`."""
+    c = np.minimum(np.asarray(costs, dtype=np.float32), np.float32(MAXCOST))
+    pad = max(0, n_best - c.shape[-1])
+    if pad:
+        c = np.concatenate([c, np.full(c.shape[:-1] + (pad,), np.inf, np.float32)], axis=-1)
+    return np.sort(c, axis=-1)[..., :n_best]
+
+
+def merge_topn(gathered: np.ndarray, n_best: int) -> np.ndarray:
+    """gathered: [world, ..., n_best] ascending lists.  Returns the combined cost exactly as `shard_merge` /
+    pmCostMultiview_cu (COMB_BEST_N) do: the n_best smallest valid (< MAXCOST) costs summed in ascending order in
+    float32, divided by their count; MAXCOST if none."""
+    g = np.moveaxis(np.asarray(gathered, dtype=np.float32), 0, -2)          # [..., world, n_best]
+    flat = np.sort(g.reshape(g.shape[:-2] + (-1,)), axis=-1)[..., :n_best]
+    valid = flat < np.float32(MAXCOST)
+    total = np.zeros(flat.shape[:-1], np.float32)
+    for i in range(flat.shape[-1]):                                          # ascending, float32, like the device loop
+        total = np.where(valid[..., i], (total + np.where(valid[..., i], flat[..., i], 0)).astype(np.float32), total)
+    cnt = valid.sum(axis=-1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cost = np.where(cnt > 0, total / np.maximum(cnt, 1).astype(np.float32), np.float32(MAXCOST)).astype(np.float32)
+    cost = np.where((cost != cost) | (cost > MAXCOST) | (cost < 0), np.float32(MAXCOST), cost)
+    return cost
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference-view batch
+# ----------------------------------------------------------------------------------------------------------------
+
+def run_reference_view_batch(make_scene: Callable[[int], object], n_reference_views: int, rank: int, world: int,
+                             device: int = 0, on_result: Optional[Callable] = None) -> List[float]:
+    """Run this rank's share of the reference views, one after another, on its GPU.  Returns the sweep times (ms)."""
+    from . import api
+    times = []
+    ctx = None
+    for ref in assign_reference_views(n_reference_views, rank, world):
+        sc = make_scene(ref)
+        if ctx is None or (ctx.W, ctx.H) != (sc.cols, sc.rows) or ctx.max_views < sc.n_views:
+            if ctx is not None:
+                ctx.close()
+            ctx = api.Context(sc.cols, sc.rows, sc.n_views, device=device)
+        ctx.load_scene(sc)
+        times.append(ctx.run())
+        if on_result is not None:
+            on_result(ref, *ctx.get_state())
+    if ctx is not None:
+        ctx.close()
+    return times
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# source-view shard
+# ----------------------------------------------------------------------------------------------------------------
+
+class ViewShardRunner:
+    """One reference view, source views sharded over the ranks of `group` (default: the world group)."""
+
+    def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None):
+        import torch
+        from . import api
+        self.torch, self.scene, self.rank, self.world, self.group = torch, scene, rank, world, group
+        self.local = partition_views(scene.n_views, world)[rank]
+        if not self.local:
+            raise ValueError("more ranks than source views")
+        self.ctx = api.Context(scene.cols, scene.rows, len(self.local), device=device)
+        ctx = self.ctx
+        ctx.set_params(scene.params)
+        ctx.set_reference(np.ascontiguousarray(scene.images[0]), scene.cameras[0])
+        for v, pos in enumerate(self.local):
+            idx = scene.subset[pos]
+            ctx.set_view(v, np.ascontiguousarray(scene.images[idx]), scene.cameras[idx])
+        ctx.set_num_views(len(self.local))
+        ctx.set_rng(seed)
+        self.dev = torch.device("cuda", device)
+        self.n_stages = ctx.shard_num_stages()
+        self.xchg = {}
+        for st in range(self.n_stages):
+            n = ctx.shard_stage_floats(st)
+            if n not in self.xchg:
+                self.xchg[n] = (torch.empty(n, dtype=torch.float32, device=self.dev),
+                                torch.empty(n * world, dtype=torch.float32, device=self.dev))
+        self.stage_floats = [ctx.shard_stage_floats(st) for st in range(self.n_stages)]
+        self.collectives = 0
+
+    def _stage(self, colour: int, stage: int):
+        import torch.distributed as dist
+        loc, gat = self.xchg[self.stage_floats[stage]]
+        self.ctx.shard_eval(colour, stage, loc)
+        if self.world > 1:
+            dist.all_gather_into_tensor(gat, loc, group=self.group)
+            self.torch.cuda.synchronize(self.dev)
+            self.collectives += 1
+        else:
+            gat.copy_(loc)
+            self.torch.cuda.synchronize(self.dev)
+        self.ctx.shard_accept(colour, stage, gat, self.world)
+
+    def run(self):
+        """runcuda() with sharded views: returns (norm4, cost) like Context.get_state after gpm_run."""
+        ctx = self.ctx
+        ctx.init_planes()                                   # identical on all ranks (same seed)
+        self._stage(0, 0)                                   # initial costs over all views
+        for _ in range(self.scene.params.iterations):
+            for colour in (0, 1):
+                for stage in range(1, self.n_stages):
+                    self._stage(colour, stage)
+        ctx.finalize()
+        return ctx.get_state()
+
+    def close(self):
+        self.ctx.close()

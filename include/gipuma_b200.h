@@ -115,6 +115,21 @@ int gpm_cost_eval(gpm_ctx* ctx, const float* planes, float* out_cost, int on_dev
  * kernel to the end of the final kernel — the reference's own timed span (gipuma.cu:1908-1952). */
 int gpm_run(gpm_ctx* ctx, float* sweep_ms);
 
+/* ---- source-view sharding across GPUs (cost_comb = best_n only) --------------------------------
+ * Each rank creates a context holding ALL of the state but only ITS subset of the source views (gpm_set_view /
+ * gpm_set_num_views with the local views).  Per stage, gpm_shard_eval writes this rank's ascending n_best smallest
+ * per-view costs per pixel and hypothesis slot into `xchg_dev` (gpm_shard_stage_floats(stage) floats, device memory);
+ * the caller all-gathers the buffers of all ranks (rank-major) and hands the result to gpm_shard_accept, which merges,
+ * combines in the reference's order (gipuma.cu:779-803) and applies the accept logic.  Stages per colour:
+ * 1 (8 propagation candidates), then 2 .. gpm_shard_num_stages()-1 (refinement steps, sequential).  Stage 0 computes
+ * the initial costs after gpm_init_planes (both colours at once; `colour` ignored).  Results are bit-identical to a
+ * single-GPU run over all views. */
+int gpm_init_planes(gpm_ctx* ctx);
+int gpm_shard_num_stages(gpm_ctx* ctx);
+long long gpm_shard_stage_floats(gpm_ctx* ctx, int stage);
+int gpm_shard_eval(gpm_ctx* ctx, int colour, int stage, float* xchg_dev);
+int gpm_shard_accept(gpm_ctx* ctx, int colour, int stage, const float* gathered_dev, int world);
+
 /* Counters of the last gpm_sweep/gpm_run: [0] kernels launched, [1] hypotheses offered,
  * [2] hypotheses skipped as exact duplicates / out of depth range, [3] hypotheses cut short by the
  * exact lower bound, [4] (view,sample) evaluations done, [5] (view,sample) evaluations a full run would do. */

@@ -1,0 +1,88 @@
+"""Source-view sharding (multi-GPU mode) on one GPU: the ranks are simulated by separate contexts holding disjoint
+view subsets; the all-gather is a torch.cat.  The merged flow must reproduce the single-context run bit for bit.
+(The NCCL plumbing itself is exercised by tools/run_shard_nccl.py under torchrun on >= 2 GPUs and by the gloo tests.)"""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _sharded_run(sc, world, seed=0xC0FFEE):
+    import torch
+    from gipuma_b200 import multigpu as M
+    runners = [M.ViewShardRunner(sc, r, 1, device=0, seed=seed) for r in range(world)]     # world=1: no dist calls inside
+    parts = M.partition_views(sc.n_views, world)
+    # re-create each runner's context with its own shard (ViewShardRunner(world=1) would take all views)
+    for r, run in enumerate(runners):
+        run.ctx.close()
+    from gipuma_b200 import api
+    ctxs = []
+    for r in range(world):
+        ctx = api.Context(sc.cols, sc.rows, len(parts[r]))
+        ctx.set_params(sc.params)
+        ctx.set_reference(np.ascontiguousarray(sc.images[0]), sc.cameras[0])
+        for v, pos in enumerate(parts[r]):
+            ctx.set_view(v, np.ascontiguousarray(sc.images[sc.subset[pos]]), sc.cameras[sc.subset[pos]])
+        ctx.set_num_views(len(parts[r]))
+        ctx.set_rng(seed)
+        ctxs.append(ctx)
+    n_stages = ctxs[0].shard_num_stages()
+
+    def stage(colour, st):
+        n = ctxs[0].shard_stage_floats(st)
+        locs = []
+        for ctx in ctxs:
+            buf = torch.empty(n, dtype=torch.float32, device="cuda")
+            ctx.shard_eval(colour, st, buf)
+            locs.append(buf)
+        gathered = torch.cat(locs)                       # rank-major, what all_gather_into_tensor produces
+        torch.cuda.synchronize()
+        for ctx in ctxs:
+            ctx.shard_accept(colour, st, gathered, world)
+
+    for ctx in ctxs:
+        ctx.init_planes()
+    stage(0, 0)
+    for _ in range(sc.params.iterations):
+        for colour in (0, 1):
+            for st in range(1, n_stages):
+                stage(colour, st)
+    outs = []
+    for ctx in ctxs:
+        ctx.finalize()
+        outs.append(ctx.get_state())
+        ctx.close()
+    return outs
+
+
+@pytest.mark.parametrize("cfg,rows,cols,views,world,box,nbest", [
+    (2, 64, 96, 6, 1, 15, 3),          # degenerate: one rank holds every view
+    (2, 64, 96, 6, 2, 15, 3),
+    (2, 96, 128, 10, 4, 11, 3),
+    (4, 64, 96, 35, 2, 7, 3),          # > 32 views in total, 18 + 17 per rank
+    (2, 64, 96, 3, 2, 9, 5),           # n_best larger than the number of views
+])
+def test_view_shard_equals_single_context(cfg, rows, cols, views, world, box, nbest):
+    from gipuma_b200 import api, scene as S
+    sc = S.make_config(cfg, rows=rows, cols=cols, n_views=views, iterations=2, seed=555)
+    sc.params.box_hsize = sc.params.box_vsize = box
+    sc.params.n_best = nbest
+    single, _, _ = api.runcuda(sc, seed=0xC0FFEE)
+    outs = _sharded_run(sc, world)
+    for n4, c in outs:                                     # every rank ends with the same, identical state
+        assert bits_equal(n4, single.norm4) == 0
+        assert bits_equal(c, single.c) == 0
+
+
+def test_view_shard_refuses_other_combinations():
+    import torch
+    from gipuma_b200 import api, scene as S
+    sc = S.make_config(1, rows=64, cols=96)
+    sc.params.cost_comb = S.COMB_GOOD
+    with api.Context(sc.cols, sc.rows, sc.n_views) as ctx:
+        ctx.load_scene(sc)
+        buf = torch.empty(ctx.shard_stage_floats(1), dtype=torch.float32, device="cuda")
+        with pytest.raises(api.GipumaError):
+            ctx.shard_eval(0, 1, buf)
