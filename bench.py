@@ -113,7 +113,7 @@ def cpu_baseline(sc, budget_s: float = 15.0) -> dict:
     evals_per_px_iter = 2 * (8 + 3)                              # hypotheses per pixel-iteration (E = 8 + S, S = 3 on DTU)
     rows = int(max(1, min(H // 2, budget_s / max(1e-6, t_row * evals_per_px_iter / 2))))
     cost = np.full((H, W), 50.0, np.float32)
-    cost[y0:y0 + rows] = o.cost_eval(pl, y0, y0 + rows)
+    cost[y0:y0 + rows] = o.cost_eval(pl, y0, y0 + rows)[y0:y0 + rows]
     t0 = time.perf_counter()
     o.sweep(pl, cost, 1, y0, y0 + rows)
     dt = time.perf_counter() - t0
