@@ -53,6 +53,11 @@ struct gpm_ctx {
     float* staging = nullptr;        // W*H floats, upload scratch
     cudaArray_t srcArr = nullptr;
     cudaTextureObject_t srcTex = 0;
+    cudaArray_t gradArr = nullptr;   // layered RG32F: (Gx, Gy) central differences of every source view (packed sampling mode)
+    cudaTextureObject_t gradTex = 0;
+    float2* gradLin = nullptr;       // W*H staging for one view's gradients
+    int* d_flag = nullptr;
+    std::vector<char> view_8bit;     // per view: every pixel an integer in [0,255]
     ViewCam* d_cams = nullptr;
     std::vector<ViewCam> h_cams;
     bool cams_dirty = true;
@@ -64,7 +69,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    int opt_cost_variant = 1;
+    int opt_cost_variant = 1, opt_packed = 1;
     int smem_optin = 0;
 };
 
@@ -113,6 +118,8 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.prune = c->opt_prune;
     P.dedupe_self = c->opt_dedupe ? 1 : 0;
     P.cost_variant = init_phase ? 0 : c->opt_cost_variant;
+    P.packed = c->opt_packed;
+    for (int v = 0; v < c->V; v++) if (!c->view_8bit[v]) P.packed = 0;
     P.dedupe_cand = c->opt_dedupe ? 1 : 0;
     P.rng_mode = c->rng_mode;
     P.ref = c->ref;
@@ -143,7 +150,7 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
 {
     const size_t smem = block_smem_bytes(P);
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_sweep<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes, c->cost, c->rng,
+    k_sweep<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
                                                       c->prov, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -184,6 +191,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     gpm_ctx* c = new gpm_ctx;
     c->device = device;  c->W = width;  c->H = height;  c->maxV = max_views;
     c->have_view.assign(max_views, 0);
+    c->view_8bit.assign(max_views, 0);
     c->h_cams.assign(max_views, ViewCam{});
     const size_t n = (size_t)width * height;
     c->refpitch = (width + 2 * GPM_APRON + 31) & ~31;
@@ -196,6 +204,8 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->cost, n * sizeof(float)));
     ok(cudaMalloc(&c->prov, n));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
+    ok(cudaMalloc(&c->gradLin, n * sizeof(float2)));
+    ok(cudaMalloc(&c->d_flag, sizeof(int)));
     ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
     ok(cudaMalloc(&c->d_cams, sizeof(ViewCam) * max_views));
     ok(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
@@ -206,6 +216,8 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
+        cudaChannelFormatDesc desc2 = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindFloat);
+        ok(cudaMalloc3DArray(&c->gradArr, &desc2, make_cudaExtent(width, height, max_views), cudaArrayLayered));
     }
     if (err == cudaSuccess) {
         cudaResourceDesc res;  memset(&res, 0, sizeof(res));
@@ -215,6 +227,8 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
         ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
+        res.res.array.array = c->gradArr;
+        ok(cudaCreateTextureObject(&c->gradTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         ok(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
@@ -236,6 +250,9 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
+    if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
+    if (c->gradArr) cudaFreeArray(c->gradArr);
+    cudaFree(c->gradLin);  cudaFree(c->d_flag);
     cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -308,14 +325,28 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     if (!c || !img || !cam) return fail(GPM_E_ARG, "gpm_set_view: null argument");
     if (v < 0 || v >= c->maxV) return fail(GPM_E_ARG, "gpm_set_view: view index out of range");
     DeviceGuard g(c->device);
-    if (pitch_bytes == 0) pitch_bytes = (size_t)c->W * sizeof(float);
+    float* d = nullptr;
+    size_t pf = 0;
+    int rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);      // host images go through the staging buffer
+    if (rc) return rc;
     cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
-    m.srcPtr = make_cudaPitchedPtr(const_cast<float*>(img), pitch_bytes, c->W, c->H);
+    m.srcPtr = make_cudaPitchedPtr(d, pf * sizeof(float), c->W, c->H);
     m.dstArray = c->srcArr;
     m.dstPos = make_cudaPos(0, 0, v);
     m.extent = make_cudaExtent(c->W, c->H, 1);
-    m.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    m.kind = cudaMemcpyDeviceToDevice;
     CU(cudaMemcpy3DAsync(&m, c->stream));
+    // central-difference planes + the "8-bit valued" test for the packed sampling mode
+    const int one = 1;
+    CU(cudaMemcpyAsync(c->d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    dim3 b(32, 8), gr((c->W + 31) / 32, (c->H + 7) / 8);
+    k_make_gradients<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->gradLin, c->d_flag);
+    CU(cudaGetLastError());
+    m.srcPtr = make_cudaPitchedPtr(c->gradLin, (size_t)c->W * sizeof(float2), c->W, c->H);
+    m.dstArray = c->gradArr;
+    CU(cudaMemcpy3DAsync(&m, c->stream));
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ViewCam& vc = c->h_cams[v];
     memcpy(vc.K, cam->K, sizeof(vc.K));
     memcpy(vc.R, cam->R, sizeof(vc.R));
@@ -323,7 +354,8 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     c->cams_dirty = true;
     c->have_view[v] = 1;
     CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    if (!on_device) CU(cudaStreamSynchronize(c->stream));   // the caller may reuse its host buffer
+    CU(cudaStreamSynchronize(c->stream));        // staging buffers are reused; the caller may reuse its buffer
+    c->view_8bit[v] = flag ? 1 : 0;
     return GPM_OK;
 }
 
@@ -366,7 +398,7 @@ static int do_init(gpm_ctx* c)
     c->launches++;
     CU(cudaGetLastError());
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes,
+    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes,
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -467,7 +499,7 @@ extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, i
         CU(cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, d_pl, d_out, nullptr);
+    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, d_pl, d_out, nullptr);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !on_device) e = cudaMemcpyAsync(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
@@ -548,7 +580,7 @@ extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev
     int rc = shard_common(c, stage, P);
     if (rc) return rc;
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_shard_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->planes, c->cost,
+    k_shard_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost,
                                                                           c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage, xchg_dev);
     c->launches++;
     CU(cudaGetLastError());
@@ -617,6 +649,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
     else if (n == "cost_variant") c->opt_cost_variant = value != 0;
+    else if (n == "packed") c->opt_packed = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;
 }

@@ -83,7 +83,7 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
 #endif
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
-            cudaTextureObject_t src, const float4* __restrict__ planes, float* __restrict__ cost,
+            cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, float* __restrict__ cost,
             unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(16) float smem[];
@@ -102,8 +102,8 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
         setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
         const float inf = __int_as_float(0x7f800000);
-        const float c = P.cost_variant ? eval_plane<true>(P, sCam, ws, src, n.x, n.y, n.z, n.w, inf, lane, st)
-                                       : eval_plane<false>(P, sCam, ws, src, n.x, n.y, n.z, n.w, inf, lane, st);
+        const float c = P.cost_variant ? eval_plane<true>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
+                                       : eval_plane<false>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
         if (lane == 0) cost[(size_t)py * P.W + px] = c;
     }
     flush_stats(stats, st, lane);
@@ -114,7 +114,7 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 // colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
-        cudaTextureObject_t src, float4* __restrict__ planes, float* __restrict__ cost,
+        cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
         unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, int colour, int phase_mask,
         unsigned long long* __restrict__ stats)
 {
@@ -184,7 +184,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
-                const float c = eval_plane<true>(P, sCam, ws, src, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                const float c = eval_plane<true>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
                     norm_now = nb;
@@ -221,7 +221,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
                     if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
                     cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
-                    const float c = eval_plane<false>(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    const float c = eval_plane<false>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
                     if (c < cost_now) {                                                          // :986-990 (no depth-range test)
                         prov_now = 0;
                         cost_now = c;
@@ -262,7 +262,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
 // ============================================================================================================
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
-             cudaTextureObject_t src, const float4* __restrict__ planes, const float* __restrict__ cost,
+             cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
              const unsigned char* __restrict__ prov, float* __restrict__ dispbuf, float4* __restrict__ candbuf,
              float* __restrict__ canddepth, int colour, int stage, float* __restrict__ xchg)
 {
@@ -295,7 +295,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
         const float4 norm_now = planes[center];
         float c0, c1;
         if (stage == 0) {
-            eval_plane<false>(P, sCam, ws, src, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
+            eval_plane<false>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         } else if (stage == 1) {
             const int prov_now = prov[center];
@@ -331,7 +331,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                     (void)prov_now;
                 }
                 if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-                eval_plane<true>(P, sCam, ws, src, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+                eval_plane<true>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
                 local_topn(P, c0, c1, lane, out + k * nb);
             }
         } else {
@@ -361,7 +361,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
             if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
             cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
             if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
-            eval_plane<false>(P, sCam, ws, src, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            eval_plane<false>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         }
     }
@@ -451,6 +451,21 @@ __global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict
     o.z = ffma(n.z, R[8], ffma(n.x, R[6], fmul(n.y, R[7])));
     o.w = (cost[center] != GPM_MAXCOST) ? plane_depth(P.ref, n.x, n.y, n.z, n.w, __int2float_rn(x), __int2float_rn(y)) : 0.0f;
     planes[center] = o;
+}
+
+// G[x,y] = (I[clamp(x+1),y] - I[clamp(x-1),y],  I[x,clamp(y+1)] - I[x,clamp(y-1)]) for the packed sampling mode, and a flag
+// that stays 1 only if every pixel is an integer in [0, 255] (the exactness condition of that mode).
+__global__ void k_make_gradients(const float* __restrict__ img, size_t pitch_floats, int W, int H, float2* __restrict__ out,
+                                 int* __restrict__ all_8bit)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float* row = img + (size_t)y * pitch_floats;
+    const float v = row[x];
+    const float gx = fsub(row[min(x + 1, W - 1)], row[max(x - 1, 0)]);
+    const float gy = fsub(img[(size_t)min(y + 1, H - 1) * pitch_floats + x], img[(size_t)max(y - 1, 0) * pitch_floats + x]);
+    out[(size_t)y * W + x] = make_float2(gx, gy);
+    if (!(v >= 0.0f && v <= 255.0f && v == rintf(v))) *all_8bit = 0;
 }
 
 // replicate-pad the reference image by GPM_APRON on every side (== the texture's clamp addressing, main.cpp:644-645)
