@@ -47,6 +47,9 @@ struct gpm_ctx {
     float* dispbuf = nullptr;        // view-shard mode: disp_now carried between the stages of one colour
     float4* candbuf = nullptr;       // view-shard mode: refinement candidate of the current step
     float* canddepth = nullptr;
+    float4* seen = nullptr;          // [H*W*8] last plane offered to each pixel from each of the 8 propagation directions
+    float4* refseen = nullptr;       // [H*W]   plane from which the last all-rejected refinement started
+    unsigned short* memo_mask = nullptr;   // [H*W] validity bits of seen (0-7) and refseen (8)
     unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
     int refpitch = 0;
@@ -69,7 +72,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    int opt_cost_variant = 1, opt_packed = 1;
+    int opt_cost_variant = 1, opt_packed = 1, opt_memo = 1;
     int smem_optin = 0;
 };
 
@@ -118,6 +121,7 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.prune = c->opt_prune;
     P.dedupe_self = c->opt_dedupe ? 1 : 0;
     P.cost_variant = init_phase ? 0 : c->opt_cost_variant;
+    P.memo = c->opt_memo;
     P.packed = c->opt_packed;
     for (int v = 0; v < c->V; v++) if (!c->view_8bit[v]) P.packed = 0;
     P.dedupe_cand = c->opt_dedupe ? 1 : 0;
@@ -133,6 +137,12 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     if (c->opt_nwarps > 0) nw = c->opt_nwarps;
     if (nw > GPM_LB_THREADS / 32) nw = GPM_LB_THREADS / 32;
     P.nwarps = nw;
+    if (P.packed && c->opt_packed == 1) {
+        // auto: the packed mode triples the texture bytes a warp touches per pixel (4 -> 12 B per texel and view); it only
+        // pays while the block's working set stays near the L1 (measured: +11 % at cfg 2, -17 % at cfg 3)
+        const size_t ws = (size_t)P.V * (box + 2) * (box + 2) * 12 * nw;
+        if (ws > 640 * 1024) P.packed = 0;
+    }
     if (block_smem_bytes(P) > (size_t)c->smem_optin)
         return fail(GPM_E_ARG, "configuration needs more shared memory per block than the device offers");
     return GPM_OK;
@@ -150,8 +160,8 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
 {
     const size_t smem = block_smem_bytes(P);
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_sweep<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
-                                                      c->prov, colour, mask, c->opt_stats ? c->d_stats : nullptr);
+    (P.packed ? k_sweep<true> : k_sweep<false>)<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
+                                                      c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
     return GPM_OK;
@@ -203,6 +213,9 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->planes, n * sizeof(float4)));
     ok(cudaMalloc(&c->cost, n * sizeof(float)));
     ok(cudaMalloc(&c->prov, n));
+    ok(cudaMalloc(&c->seen, n * 8 * sizeof(float4)));
+    ok(cudaMalloc(&c->refseen, n * sizeof(float4)));
+    ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned short)));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
     ok(cudaMalloc(&c->gradLin, n * sizeof(float2)));
     ok(cudaMalloc(&c->d_flag, sizeof(int)));
@@ -213,6 +226,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaMemsetAsync(c->planes, 0, n * sizeof(float4), c->stream));      // LineState::resize zeroes (linestate.h:19-24)
         ok(cudaMemsetAsync(c->cost, 0, n * sizeof(float), c->stream));
         ok(cudaMemsetAsync(c->prov, 2, n, c->stream));
+        ok(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned short), c->stream));
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
@@ -230,9 +244,12 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         res.res.array.array = c->gradArr;
         ok(cudaCreateTextureObject(&c->gradTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        ok(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_cost_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
     }
     if (err != cudaSuccess) {
         std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
@@ -253,7 +270,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
     if (c->gradArr) cudaFreeArray(c->gradArr);
     cudaFree(c->gradLin);  cudaFree(c->d_flag);
-    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->seen);  cudaFree(c->refseen);  cudaFree(c->memo_mask);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -272,6 +289,10 @@ extern "C" int gpm_set_params(gpm_ctx* c, const gpm_params* p)
     if (p->iterations < 0) return fail(GPM_E_ARG, "iterations must be >= 0");
     c->prm = *p;
     c->have_params = true;
+    {
+        DeviceGuard g(c->device);
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));   // memo depends on the parameters
+    }
     return GPM_OK;
 }
 
@@ -288,6 +309,7 @@ extern "C" int gpm_set_rng(gpm_ctx* c, unsigned long long seed, int mode)
     DeviceGuard g(c->device);
     c->seed = seed;
     c->rng_mode = mode;
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     if (mode == GPM_RNG_STATEFUL && !c->rng) {
         CU(cudaMalloc(&c->rng, (size_t)c->W * c->H * 6 * sizeof(unsigned)));
         CU(cudaMemsetAsync(c->rng, 0, (size_t)c->W * c->H * 6 * sizeof(unsigned), c->stream));
@@ -316,6 +338,7 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     r.f = cam->f;  r.f_cam = cam->f;  r.baseline = cam->baseline;
     c->have_ref = true;
     CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
     return GPM_OK;
 }
@@ -354,6 +377,7 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     c->cams_dirty = true;
     c->have_view[v] = 1;
     CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));        // staging buffers are reused; the caller may reuse its buffer
     c->view_8bit[v] = flag ? 1 : 0;
     return GPM_OK;
@@ -370,6 +394,7 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     // provenance of the supplied costs is unknown (2) unless the caller vouches that they came from an
     // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
     CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? 0 : 2, n, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
@@ -398,11 +423,12 @@ static int do_init(gpm_ctx* c)
     c->launches++;
     CU(cudaGetLastError());
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes,
+    (P.packed ? k_cost_eval<true> : k_cost_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes,
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(c->prov, 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     return GPM_OK;
 }
 
@@ -431,7 +457,8 @@ static int do_finalize(gpm_ctx* c)
     k_finalize<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));   // planes are world-frame outputs now
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));   // planes are world-frame outputs now
     return GPM_OK;
 }
 
@@ -499,7 +526,7 @@ extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, i
         CU(cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_cost_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, d_pl, d_out, nullptr);
+    (P.packed ? k_cost_eval<true> : k_cost_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, d_pl, d_out, nullptr);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !on_device) e = cudaMemcpyAsync(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
@@ -580,7 +607,7 @@ extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev
     int rc = shard_common(c, stage, P);
     if (rc) return rc;
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    k_shard_eval<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost,
+    (P.packed ? k_shard_eval<true> : k_shard_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost,
                                                                           c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage, xchg_dev);
     c->launches++;
     CU(cudaGetLastError());
@@ -649,7 +676,8 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
     else if (n == "cost_variant") c->opt_cost_variant = value != 0;
-    else if (n == "packed") c->opt_packed = value != 0;
+    else if (n == "packed") c->opt_packed = value;            // 0 off, 1 auto (default), 2 force
+    else if (n == "memo") c->opt_memo = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;
 }

@@ -81,6 +81,7 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
 #define GPM_LB_THREADS 512       // max threads per block of the warp-per-pixel kernels (16 warps)
 #define GPM_LB_BLOCKS 1
 #endif
+template <bool PACKED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
             cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, float* __restrict__ cost,
@@ -102,8 +103,8 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
         setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
         const float inf = __int_as_float(0x7f800000);
-        const float c = P.cost_variant ? eval_plane<true>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
-                                       : eval_plane<false>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
+        const float c = P.cost_variant ? eval_plane<true, PACKED>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
+                                       : eval_plane<false, PACKED>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
         if (lane == 0) cost[(size_t)py * P.W + px] = c;
     }
     flush_stats(stats, st, lane);
@@ -112,10 +113,12 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 // ---- one checkerboard colour: close + far propagation + refinement, fused --------------------
 // gipuma_{black,red}_spatialPropClose_cu / spatialPropFar_cu / planeRefine_cu, gipuma.cu:1353-1823.
 // colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
+template <bool PACKED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
-        unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, int colour, int phase_mask,
+        unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, float4* __restrict__ seen,
+        float4* __restrict__ refseen, unsigned short* __restrict__ memo_mask, int colour, int phase_mask,
         unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(16) float smem[];
@@ -165,9 +168,22 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 mine_ok = ok && phase_on;
                 if (mine_ok) mine = planes[(size_t)qy * W + qx];
             }
+            // Memo of rejected work.  A pixel's cost only ever decreases (gipuma.cu:867,986), and cost(p, plane) is a pure
+            // function, so a neighbour plane this pixel has already been offered — accepted or not — can never be
+            // accepted later: seen[p][k] holds the last plane offered from direction k; an unchanged neighbour is skipped
+            // without evaluation, in every later iteration.  Exact, not a heuristic.
+            unsigned short mmask = P.memo ? memo_mask[center] : (unsigned short)0;
+            bool memo_hit = false;
+            if (P.memo && mine_ok && ((mmask >> lane) & 1)) {
+                const float4 old = seen[center * 8 + lane];
+                memo_hit = __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
+                           __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
+            }
+            const unsigned memo_bits = __ballot_sync(GPM_FULL, memo_hit);
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
             for (int k = 0; k < 8; k++) {
                 if (!((cand_mask >> k) & 1)) continue;
+                if ((memo_bits >> k) & 1) { st.skip++; continue; }
                 float4 nb;
                 nb.x = __shfl_sync(GPM_FULL, mine.x, k);  nb.y = __shfl_sync(GPM_FULL, mine.y, k);
                 nb.z = __shfl_sync(GPM_FULL, mine.z, k);  nb.w = __shfl_sync(GPM_FULL, mine.w, k);
@@ -184,7 +200,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
-                const float c = eval_plane<true>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                const float c = eval_plane<true, PACKED>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
                     norm_now = nb;
@@ -193,7 +209,25 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 }
             }
 
-            if (phase_mask & 4) {
+            if (P.memo && mine_ok && !memo_hit) {            // every candidate offered above is now known to this pixel
+                seen[center * 8 + lane] = mine;
+            }
+            unsigned short new_mask = (unsigned short)(mmask | (cand_mask & 0xffu));
+            // The refinement candidates are a pure function of (pixel, plane at refinement start) in GPM_RNG_REFERENCE
+            // mode (zero-state stream; disp_now == plane_depth(norm_now) here), so a refinement that rejected all its steps
+            // from exactly this plane before would reject them again.
+            bool refine = (phase_mask & 4) != 0;
+            if (refine && P.memo && P.rng_mode == 0 && ((mmask >> 8) & 1)) {
+                const float4 old = refseen[center];
+                if (__float_as_uint(old.x) == __float_as_uint(norm_now.x) && __float_as_uint(old.y) == __float_as_uint(norm_now.y) &&
+                    __float_as_uint(old.z) == __float_as_uint(norm_now.z) && __float_as_uint(old.w) == __float_as_uint(norm_now.w)) {
+                    refine = false;
+                    st.skip += 3;
+                }
+            }
+            if (refine) {
+                const float4 norm_start = norm_now;
+                bool any_accept = false;
                 // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
                 Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};       // GPM_RNG_REFERENCE: gs.cs is never written (gipuma.cu:1840,1608)
                 if (P.rng_mode == 1) {
@@ -221,9 +255,10 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
                     if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
                     cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
-                    const float c = eval_plane<false>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    const float c = eval_plane<false, PACKED>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
                     if (c < cost_now) {                                                          // :986-990 (no depth-range test)
                         prov_now = 0;
+                        any_accept = true;
                         cost_now = c;
                         disp_now = depth_new;
                         norm_now = cand;
@@ -234,7 +269,12 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     unsigned* o = rng_state + center * 6;
                     o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
                 }
+                if (P.memo && P.rng_mode == 0) {
+                    if (!any_accept) { if (lane == 0) refseen[center] = norm_start;  new_mask |= 0x100; }
+                    else new_mask &= (unsigned short)~0x100;
+                }
             }
+            if (P.memo && lane == 0 && new_mask != mmask) memo_mask[center] = new_mask;
             if (lane == 0) {                                                                     // :1585-1587
                 cost[center] = cost_now;
                 planes[center] = norm_now;
@@ -260,6 +300,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
 //   stage 2 + s    refinement step s                         (1 slot; sequential: step s+1 depends on step s' accept)
 // Exchange index of pixel (x, y): y * ceil(W/2) + x/2 (pixels of one colour have distinct x/2 within a row).
 // ============================================================================================================
+template <bool PACKED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
              cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
@@ -295,7 +336,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
         const float4 norm_now = planes[center];
         float c0, c1;
         if (stage == 0) {
-            eval_plane<false>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
+            eval_plane<false, PACKED>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         } else if (stage == 1) {
             const int prov_now = prov[center];
@@ -331,7 +372,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                     (void)prov_now;
                 }
                 if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-                eval_plane<true>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+                eval_plane<true, PACKED>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
                 local_topn(P, c0, c1, lane, out + k * nb);
             }
         } else {
@@ -361,7 +402,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
             if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
             cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
             if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
-            eval_plane<false>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            eval_plane<false, PACKED>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         }
     }

@@ -130,6 +130,6 @@ def test_packed_path_exact_on_border_heavy_scene():
     sc.params.box_hsize = sc.params.box_vsize = 21
     ref = _ref(sc.n_views)
     r_n4, r_c, _, _ = ref.run(sc, seed=123)
-    for opts in ({}, {"packed": 0}):
+    for opts in ({"packed": 2}, {"packed": 0}, {"memo": 0}):
         ls, _, _ = api.runcuda(sc, seed=123, options=opts)
         assert bits_equal(ls.norm4, r_n4) == 0 and bits_equal(ls.c, r_c) == 0

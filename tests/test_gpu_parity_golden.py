@@ -70,7 +70,7 @@ def test_separate_phase_launches_match_too(golden, name):
 
 
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("opts", [{}, {"prune": 0, "dedupe": 0}, {"packed": 0}])
+@pytest.mark.parametrize("opts", [{}, {"prune": 0, "dedupe": 0, "memo": 0}, {"packed": 0}, {"packed": 2}, {"memo": 0}])
 def test_full_run_matches_reference_runcuda(golden, name, opts):
     from gipuma_b200 import api
     sc, z = golden[name]
@@ -91,7 +91,7 @@ def test_exact_pruning_and_dedupe_actually_skip_work(golden):
     name = golden_names()[0]
     sc, z = golden[name]
     _, _, st_on = api.runcuda(sc, seed=0xC0FFEE)
-    _, _, st_off = api.runcuda(sc, seed=0xC0FFEE, options={"prune": 0, "dedupe": 0})
+    _, _, st_off = api.runcuda(sc, seed=0xC0FFEE, options={"prune": 0, "dedupe": 0, "memo": 0})
     assert st_off["pruned"] == 0 and st_off["pairs"] == st_off["pairs_full"]
     assert st_on["pairs"] < st_off["pairs"] and st_on["skipped"] > st_off["skipped"]
 

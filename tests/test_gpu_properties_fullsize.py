@@ -36,7 +36,7 @@ def test_cfg2_full_size_invariants(cfg2):
     a, ms_a, st_a = api.runcuda(sc)
     b, ms_b, st_b = api.runcuda(sc)
     assert bits_equal(a.norm4, b.norm4) == 0 and bits_equal(a.c, b.c) == 0            # deterministic
-    c, ms_c, st_c = api.runcuda(sc, options={"prune": 0, "dedupe": 0})
+    c, ms_c, st_c = api.runcuda(sc, options={"prune": 0, "dedupe": 0, "memo": 0, "packed": 0})
     assert bits_equal(a.norm4, c.norm4) == 0 and bits_equal(a.c, c.c) == 0            # pruning/dedupe are exact
     assert st_c["pairs"] == st_c["pairs_full"] and st_a["pairs"] < st_c["pairs"]
     depth = a.norm4[..., 3]
