@@ -72,7 +72,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    int opt_cost_variant = 1, opt_packed = 1, opt_memo = 1;
+    int opt_cost_variant = 1, opt_packed = 0, opt_memo = 1;
     int smem_optin = 0;
 };
 
@@ -676,7 +676,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
     else if (n == "cost_variant") c->opt_cost_variant = value != 0;
-    else if (n == "packed") c->opt_packed = value;            // 0 off, 1 auto (default), 2 force
+    else if (n == "packed") c->opt_packed = value;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

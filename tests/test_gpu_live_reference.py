@@ -109,9 +109,8 @@ def test_every_kernel_of_one_iteration_vs_live_reference():
         assert bits_equal(m4, n4) == 0
 
 
-def test_non_8bit_images_take_the_generic_five_fetch_path_and_stay_exact():
-    """The packed-gradient sampling mode is only engaged for 8-bit-valued source images (its exactness condition);
-    arbitrary float images must fall back to the reference's five fetches — and still match bit for bit."""
+def test_non_8bit_images_stay_exact():
+    """Arbitrary (non-8-bit) float images."""
     from gipuma_b200 import api, scene as S
     sc = S.make_config(2, rows=96, cols=128, n_views=5, iterations=2, seed=2024)
     rng = np.random.default_rng(9)
@@ -122,14 +121,13 @@ def test_non_8bit_images_take_the_generic_five_fetch_path_and_stay_exact():
     assert bits_equal(ls.norm4, r_n4) == 0 and bits_equal(ls.c, r_c) == 0
 
 
-def test_packed_path_exact_on_border_heavy_scene():
-    """Small image, large window, strongly tilted random planes: many samples project onto or beyond the image
-    border, where the packed mode must hand over to the five-fetch path lane by lane."""
+def test_border_heavy_scene():
+    """Small image, large window, strongly tilted random planes: many samples project onto or beyond the image border."""
     from gipuma_b200 import api, scene as S
     sc = S.make_config(2, rows=64, cols=64, n_views=4, iterations=3, seed=31)
     sc.params.box_hsize = sc.params.box_vsize = 21
     ref = _ref(sc.n_views)
     r_n4, r_c, _, _ = ref.run(sc, seed=123)
-    for opts in ({"packed": 2}, {"packed": 0}, {"memo": 0}):
+    for opts in ({}, {"memo": 0}):
         ls, _, _ = api.runcuda(sc, seed=123, options=opts)
         assert bits_equal(ls.norm4, r_n4) == 0 and bits_equal(ls.c, r_c) == 0

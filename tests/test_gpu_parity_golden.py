@@ -70,7 +70,7 @@ def test_separate_phase_launches_match_too(golden, name):
 
 
 @pytest.mark.parametrize("name", golden_names())
-@pytest.mark.parametrize("opts", [{}, {"prune": 0, "dedupe": 0, "memo": 0}, {"packed": 0}, {"packed": 2}, {"memo": 0}])
+@pytest.mark.parametrize("opts", [{}, {"prune": 0, "dedupe": 0, "memo": 0}, {"memo": 0}, {"prune": 0}])
 def test_full_run_matches_reference_runcuda(golden, name, opts):
     from gipuma_b200 import api
     sc, z = golden[name]
