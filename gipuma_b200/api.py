@@ -77,6 +77,12 @@ def load_library():
     L.gpm_reset_stats.argtypes = [vp]
     L.gpm_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.gpm_stream.argtypes = [vp]
+    L.gpm_prepare_cameras.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.POINTER(GpmCamera)]
+    L.gpm_select_views.argtypes = [C.POINTER(GpmCamera), C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                   C.POINTER(C.c_int), fp]
+    L.gpm_write_dmb.argtypes = [C.c_char_p, fp, C.c_int, C.c_int, C.c_int]
+    L.gpm_read_dmb.argtypes = [C.c_char_p, fp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.gpm_write_result_dmb.argtypes = [C.c_char_p, C.c_char_p, fp, C.c_int, C.c_int]
     L.gpm_init_planes.argtypes = [vp]
     L.gpm_shard_num_stages.argtypes = [vp]
     L.gpm_shard_stage_floats.argtypes = [vp, C.c_int]
@@ -87,7 +93,8 @@ def load_library():
     for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_num_views",
                  "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
                  "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option",
-                 "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_eval", "gpm_shard_accept"):
+                 "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_eval", "gpm_shard_accept",
+                 "gpm_prepare_cameras", "gpm_select_views", "gpm_write_dmb", "gpm_read_dmb", "gpm_write_result_dmb"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -297,3 +304,54 @@ def runcuda(scene, seed: int = 0xC0FFEE, rng_mode: int = GPM_RNG_REFERENCE, devi
         n4, c = ctx.get_state()
         st = ctx.stats()
     return LineState(n4, c), ms, st
+
+
+# ---- host-side rows of SURVEY.md §8f (no GPU needed) ---------------------------------------------------------------
+
+def prepare_cameras(Ps, cam_scale: float = 1.0):
+    """C++ restatement of getCameraParameters (cameraGeometryUtils.h:174-353): list of 3x4 projections -> GpmCamera[]."""
+    lib = load_library()
+    P = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64) for p in Ps]).reshape(-1))
+    out = (GpmCamera * len(Ps))()
+    rc = lib.gpm_prepare_cameras(P.ctypes.data_as(C.POINTER(C.c_double)), len(Ps), float(cam_scale), out)
+    if rc != 0:
+        raise GipumaError("gpm_prepare_cameras failed: %d" % rc)
+    return out
+
+
+def select_views(cams, cols: int, rows: int, min_angle: float, max_angle: float, max_views: int):
+    """Deterministic selectViews (main.cpp:430-499).  Returns (subset, (depth_min, depth_max))."""
+    lib = load_library()
+    sub = (C.c_int * max(1, len(cams)))()
+    rng = (C.c_float * 2)()
+    n = lib.gpm_select_views(cams, len(cams), cols, rows, min_angle, max_angle, max_views, sub, rng)
+    if n < 0:
+        raise GipumaError("gpm_select_views failed: %d" % n)
+    return [sub[i] for i in range(n)], (rng[0], rng[1])
+
+
+def write_dmb(path: str, data: np.ndarray):
+    a = np.ascontiguousarray(data, dtype=np.float32)
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    rc = load_library().gpm_write_dmb(path.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0], a.shape[1], ch)
+    if rc != 0:
+        raise GipumaError("gpm_write_dmb failed")
+
+
+def read_dmb(path: str) -> np.ndarray:
+    lib = load_library()
+    r, c, ch = C.c_int(), C.c_int(), C.c_int()
+    if lib.gpm_read_dmb(path.encode(), None, 0, C.byref(r), C.byref(c), C.byref(ch)) != 0:
+        raise GipumaError("gpm_read_dmb: cannot read %s" % path)
+    out = np.empty((r.value, c.value, ch.value), dtype=np.float32)
+    if lib.gpm_read_dmb(path.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), out.size, C.byref(r), C.byref(c), C.byref(ch)) != 0:
+        raise GipumaError("gpm_read_dmb: short file %s" % path)
+    return out[..., 0] if ch.value == 1 else out
+
+
+def write_result_dmb(depth_path: str, normal_path: str, norm4: np.ndarray):
+    a = np.ascontiguousarray(norm4, dtype=np.float32)
+    rc = load_library().gpm_write_result_dmb(depth_path.encode(), normal_path.encode(), a.ctypes.data_as(C.POINTER(C.c_float)),
+                                             a.shape[0], a.shape[1])
+    if rc != 0:
+        raise GipumaError("gpm_write_result_dmb failed")

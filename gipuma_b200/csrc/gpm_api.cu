@@ -217,7 +217,6 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->refseen, n * sizeof(float4)));
     ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned short)));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
-    ok(cudaMalloc(&c->gradLin, n * sizeof(float2)));
     ok(cudaMalloc(&c->d_flag, sizeof(int)));
     ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
     ok(cudaMalloc(&c->d_cams, sizeof(ViewCam) * max_views));
@@ -230,8 +229,6 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
-        cudaChannelFormatDesc desc2 = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindFloat);
-        ok(cudaMalloc3DArray(&c->gradArr, &desc2, make_cudaExtent(width, height, max_views), cudaArrayLayered));
     }
     if (err == cudaSuccess) {
         cudaResourceDesc res;  memset(&res, 0, sizeof(res));
@@ -241,8 +238,6 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
         ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
-        res.res.array.array = c->gradArr;
-        ok(cudaCreateTextureObject(&c->gradTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         ok(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
@@ -359,7 +354,19 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     m.extent = make_cudaExtent(c->W, c->H, 1);
     m.kind = cudaMemcpyDeviceToDevice;
     CU(cudaMemcpy3DAsync(&m, c->stream));
-    // central-difference planes + the "8-bit valued" test for the packed sampling mode
+    c->view_8bit[v] = 0;
+    if (c->opt_packed) {                         // experimental packed sampling mode: central-difference planes + "8-bit valued" test
+    if (!c->gradArr) {
+        cudaChannelFormatDesc desc2 = cudaCreateChannelDesc(32, 32, 0, 0, cudaChannelFormatKindFloat);
+        CU(cudaMalloc3DArray(&c->gradArr, &desc2, make_cudaExtent(c->W, c->H, c->maxV), cudaArrayLayered));
+        cudaResourceDesc res;  memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;  res.res.array.array = c->gradArr;
+        cudaTextureDesc td;  memset(&td, 0, sizeof(td));
+        td.addressMode[0] = cudaAddressModeWrap;  td.addressMode[1] = cudaAddressModeWrap;  td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&c->gradTex, &res, &td, NULL));
+        CU(cudaMalloc(&c->gradLin, (size_t)c->W * c->H * sizeof(float2)));
+    }
     const int one = 1;
     CU(cudaMemcpyAsync(c->d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     dim3 b(32, 8), gr((c->W + 31) / 32, (c->H + 7) / 8);
@@ -370,6 +377,9 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     CU(cudaMemcpy3DAsync(&m, c->stream));
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->view_8bit[v] = flag ? 1 : 0;
+    }
     ViewCam& vc = c->h_cams[v];
     memcpy(vc.K, cam->K, sizeof(vc.K));
     memcpy(vc.R, cam->R, sizeof(vc.R));
@@ -379,7 +389,6 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
     CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));        // staging buffers are reused; the caller may reuse its buffer
-    c->view_8bit[v] = flag ? 1 : 0;
     return GPM_OK;
 }
 
@@ -676,7 +685,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
     else if (n == "cost_variant") c->opt_cost_variant = value != 0;
-    else if (n == "packed") c->opt_packed = value;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
+    else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

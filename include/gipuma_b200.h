@@ -149,6 +149,19 @@ int gpm_set_option(gpm_ctx* ctx, const char* name, int value);
 /* The CUDA stream all work of this context is enqueued on (as a void*), for event timing by callers. */
 void* gpm_stream(gpm_ctx* ctx);
 
+/* ---- callers and data formats either side of the hot path (plain host C++, no CUDA) ------
+ * gpm_prepare_cameras: n row-major 3x4 projection matrices (index 0 = reference) -> the Camera_cu field values, without
+ *   OpenCV (cameraGeometryUtils.h:174-353: RQ decomposition, re-basing so that the reference is K[I|0], baseline 0.54).
+ * gpm_select_views: deterministic selectViews (main.cpp:430-499); returns the number of views written to `subset`.
+ * gpm_write_dmb / gpm_read_dmb / gpm_write_result_dmb: the .dmb depth / normal maps consumed by `fusibile`
+ *   (fileIoUtils.h:247-368; scripts/dtu_fast.sh:57). */
+int gpm_prepare_cameras(const double* P, int n, double cam_scale, gpm_camera* out);
+int gpm_select_views(const gpm_camera* cams, int n, int cols, int rows, float min_angle, float max_angle, int max_views,
+                     int* subset, float* depth_range);
+int gpm_write_dmb(const char* path, const float* data, int rows, int cols, int channels);
+int gpm_read_dmb(const char* path, float* data, size_t capacity_floats, int* rows, int* cols, int* channels);
+int gpm_write_result_dmb(const char* depth_path, const char* normal_path, const float* norm4, int rows, int cols);
+
 const char* gpm_last_error(void);
 const char* gpm_version(void);
 
