@@ -86,6 +86,46 @@ __global__ void bench_kernel(cudaTextureObject_t t1, cudaTextureObject_t t4, cud
     if (acc == 12345.678f) sink[0] = acc;
 }
 
+// lane-arrangement probe: 32 lanes = COLS x ROWS samples (ROWS = 1 << LR) at `stride` pixels, 5 R32F fetches each
+template <int LR>
+__global__ void shape_kernel(cudaTextureObject_t t1, int W, int H, int reps, float stride, float* sink)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = tid >> 5;
+    const float dx = stride * (float)(lane >> LR), dy = stride * (float)(lane & ((1 << LR) - 1));
+    float acc = 0.f;
+    for (int r = 0; r < reps; r++) {
+        uint32_t h = hash32((uint32_t)warp * 977u + r * 131071u);
+        float bx = 40.f + (float)(h % (uint32_t)(W - 160)) + (float)((h >> 20) & 255) * (1.f / 256.f);
+        float by = 40.f + (float)((h >> 8) % (uint32_t)(H - 160)) + (float)((h >> 12) & 255) * (1.f / 256.f);
+        float x = bx + 1.03f * dx + 0.05f * dy, y = by - 0.04f * dx + 0.98f * dy;
+        float c = tex2D<float>(t1, x + 0.5f, y + 0.5f);
+        float gx = tex2D<float>(t1, x + 1 + 0.5f, y + 0.5f) - tex2D<float>(t1, x - 1 + 0.5f, y + 0.5f);
+        float gy = tex2D<float>(t1, x + 0.5f, y + 1 + 0.5f) - tex2D<float>(t1, x + 0.5f, y - 1 + 0.5f);
+        acc += c + fabsf(gx) + fabsf(gy);
+    }
+    if (acc == 12345.678f) sink[0] = acc;
+}
+
+template <int LR>
+static void run_shape(cudaTextureObject_t t1, int W, int H, float stride, float* sink)
+{
+    const int blocks = 148 * 16, threads = 256, reps = 512;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    shape_kernel<LR><<<blocks, threads>>>(t1, W, H, reps, stride, sink);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 3; i++) shape_kernel<LR><<<blocks, threads>>>(t1, W, H, reps, stride, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fetches = (double)blocks * threads * reps * 5 * 3;
+    printf("shape %2d cols x %2d rows, stride %.0f px : %7.2f Gfetch/s  %.2f fetch/clk/SM  (%.1f clk per warp-fetch @1.9GHz)\n",
+           32 >> LR, 1 << LR, stride, fetches / (ms * 1e6), fetches / (ms * 1e-3) / 148.0 / 1.9e9,
+           32.0 / (fetches / (ms * 1e-3) / 148.0 / 1.9e9));
+}
+
 // exactness probe: random coordinates (interior), compare bitwise
 __global__ void exact_kernel(cudaTextureObject_t t1, cudaTextureObject_t t4, cudaTextureObject_t th,
                              int W, int H, int n, unsigned long long* counts, float* examples)
@@ -204,6 +244,11 @@ int main()
         printf("   ex: x=%.6f y=%.6f  c=%.8f/%.8f gx=%.8f/%.8f gy=%.8f/%.8f\n", he[k * 8], he[k * 8 + 1], he[k * 8 + 2], he[k * 8 + 3],
                he[k * 8 + 4], he[k * 8 + 5], he[k * 8 + 6], he[k * 8 + 7]);
 
+    // lane arrangements (what a warp-level texture instruction costs as a function of the lanes' footprint)
+    for (float stride : {2.f, 1.f}) {
+        run_shape<0>(t1, W, H, stride, sink); run_shape<1>(t1, W, H, stride, sink); run_shape<2>(t1, W, H, stride, sink);
+        run_shape<3>(t1, W, H, stride, sink); run_shape<4>(t1, W, H, stride, sink); run_shape<5>(t1, W, H, stride, sink);
+    }
     // throughput
     run_bench<0, 0>("5 x R32F bilinear", t1, t4, th, W, H, sink);
     run_bench<4, 0>("1 x R32F bilinear", t1, t4, th, W, H, sink);
