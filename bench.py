@@ -94,8 +94,9 @@ def make_scene(config: int, rank: int):
 
 def algorithmic_bytes_per_sweep_launch(W, H, V):
     """one k_sweep launch = one colour (W*H/2 pixels): own plane+cost read and written (2*20 B),
-    8 neighbour planes (8*16 B), and each image plane (reference + V sources) streamed once (4 B/pixel each)."""
-    return (W * H // 2) * (40 + 128) + (1 + V) * W * H * 4
+    8 neighbour planes (8*16 B), the memo of rejected work read (8*16 + 16 + 2 B; its writes are data dependent and not
+    counted), and each image plane (reference + V sources) streamed once (4 B/pixel each)."""
+    return (W * H // 2) * (40 + 128 + 146) + (1 + V) * W * H * 4
 
 
 def cpu_baseline(sc, budget_s: float = 15.0) -> dict:
@@ -212,12 +213,13 @@ def run_ours(args, rank, world, local):
                 "d2h_bytes_per_step": int(W * H * 20), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": 208.6e6,
+                     "traffic": 446.3e6,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "kernel": "gpm::k_sweep", "avg_launch_ms": avg_launch_ms,
                      "algorithmic_bytes_per_launch": algorithmic_bytes_per_sweep_launch(W, H, V),
-                     "note": "this path is bound by the L1TEX data pipe, not HBM: ncu l1tex__data_pipe_tex_wavefronts = 95.8 % of "
-                             "peak for this kernel (profiles/r01_ncu_k_sweep_cfg2_iter2_black.txt); traffic = ncu dram bytes of one launch"},
+                     "note": "this path is bound by the L1TEX data pipe, not HBM: ncu l1tex__data_pipe_tex_wavefronts = 95.3 % of "
+                             "peak for this kernel (profiles/r01_ncu_k_sweep_cfg2_iter2_black.txt); traffic = ncu dram bytes of that launch "
+                             "(iteration 2, black; later launches move less)"},
         "work": {"hypotheses_evaluated": stats["hypotheses"], "hypotheses_skipped_exact": stats["skipped"],
                  "hypotheses_pruned_exact": stats["pruned"], "view_samples": stats["pairs"]},
         "clocks": clocks,

@@ -126,6 +126,53 @@ static void run_shape(cudaTextureObject_t t1, int W, int H, float stride, float*
            32.0 / (fetches / (ms * 1e-3) / 148.0 / 1.9e9));
 }
 
+// layered-array variant of the 4 cols x 8 rows shape (what gpm::eval_plane issues), with a homography-like scale
+template <bool LAYERED>
+__global__ void layered_kernel(cudaTextureObject_t t1, cudaTextureObject_t tl, int W, int H, int reps, float scale, int nlayers, float* sink)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = tid >> 5;
+    const float dx = 2.f * (float)(lane >> 3), dy = 2.f * (float)(lane & 7);
+    float acc = 0.f;
+    for (int r = 0; r < reps; r++) {
+        uint32_t h = hash32((uint32_t)warp * 977u + r * 131071u);
+        float bx = 60.f + (float)(h % (uint32_t)(W - 200)) + (float)((h >> 20) & 255) * (1.f / 256.f);
+        float by = 60.f + (float)((h >> 8) % (uint32_t)(H - 200)) + (float)((h >> 12) & 255) * (1.f / 256.f);
+        float x = bx + scale * (1.0f * dx + 0.15f * dy), y = by + scale * (-0.12f * dx + 0.98f * dy);
+        const int layer = r % nlayers;
+        float c, xp, xm, yp, ym;
+        if (LAYERED) {
+            c = tex2DLayered<float>(tl, x + 0.5f, y + 0.5f, layer);
+            xp = tex2DLayered<float>(tl, x + 1 + 0.5f, y + 0.5f, layer);  xm = tex2DLayered<float>(tl, x - 1 + 0.5f, y + 0.5f, layer);
+            yp = tex2DLayered<float>(tl, x + 0.5f, y + 1 + 0.5f, layer);  ym = tex2DLayered<float>(tl, x + 0.5f, y - 1 + 0.5f, layer);
+        } else {
+            c = tex2D<float>(t1, x + 0.5f, y + 0.5f);
+            xp = tex2D<float>(t1, x + 1 + 0.5f, y + 0.5f);  xm = tex2D<float>(t1, x - 1 + 0.5f, y + 0.5f);
+            yp = tex2D<float>(t1, x + 0.5f, y + 1 + 0.5f);  ym = tex2D<float>(t1, x + 0.5f, y - 1 + 0.5f);
+        }
+        acc += c + fabsf(xp - xm) + fabsf(yp - ym);
+    }
+    if (acc == 12345.678f) sink[0] = acc;
+}
+
+template <bool LAYERED>
+static void run_layered(cudaTextureObject_t t1, cudaTextureObject_t tl, int W, int H, float scale, int nlayers, float* sink)
+{
+    const int blocks = 148 * 16, threads = 256, reps = 512;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    layered_kernel<LAYERED><<<blocks, threads>>>(t1, tl, W, H, reps, scale, nlayers, sink);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 3; i++) layered_kernel<LAYERED><<<blocks, threads>>>(t1, tl, W, H, reps, scale, nlayers, sink);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fetches = (double)blocks * threads * reps * 5 * 3;
+    printf("%s 4x8 stride-2 patch, scale %.2f, %2d layers : %7.2f Gfetch/s  (%.1f clk per warp-fetch @1.9GHz)\n", LAYERED ? "layered" : "plain  ",
+           scale, nlayers, fetches / (ms * 1e6), 32.0 / (fetches / (ms * 1e-3) / 148.0 / 1.9e9));
+}
+
 // exactness probe: random coordinates (interior), compare bitwise
 __global__ void exact_kernel(cudaTextureObject_t t1, cudaTextureObject_t t4, cudaTextureObject_t th,
                              int W, int H, int n, unsigned long long* counts, float* examples)
@@ -248,6 +295,23 @@ int main()
     for (float stride : {2.f, 1.f}) {
         run_shape<0>(t1, W, H, stride, sink); run_shape<1>(t1, W, H, stride, sink); run_shape<2>(t1, W, H, stride, sink);
         run_shape<3>(t1, W, H, stride, sink); run_shape<4>(t1, W, H, stride, sink); run_shape<5>(t1, W, H, stride, sink);
+    }
+    {
+        const int NL = 10;
+        cudaArray_t al;
+        CK(cudaMalloc3DArray(&al, &d1, make_cudaExtent(W, H, NL), cudaArrayLayered));
+        for (int l = 0; l < NL; l++) {
+            cudaMemcpy3DParms m = {};
+            m.srcPtr = make_cudaPitchedPtr(img.data(), W * 4, W, H);
+            m.dstArray = al;  m.dstPos = make_cudaPos(0, 0, l);  m.extent = make_cudaExtent(W, H, 1);  m.kind = cudaMemcpyHostToDevice;
+            CK(cudaMemcpy3D(&m));
+        }
+        cudaTextureObject_t tl = make_tex(al);
+        for (float sc : {1.0f, 1.3f, 0.8f}) {
+            run_layered<false>(t1, tl, W, H, sc, 1, sink);
+            run_layered<true>(t1, tl, W, H, sc, 1, sink);
+            run_layered<true>(t1, tl, W, H, sc, NL, sink);
+        }
     }
     // throughput
     run_bench<0, 0>("5 x R32F bilinear", t1, t4, th, W, H, sink);
