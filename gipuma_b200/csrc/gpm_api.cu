@@ -617,7 +617,7 @@ extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev
     if (rc) return rc;
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
     (P.packed ? k_shard_eval<true> : k_shard_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost,
-                                                                          c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage, xchg_dev);
+                                                                          c->prov, c->dispbuf, c->candbuf, c->canddepth, c->seen, c->memo_mask, colour, stage, xchg_dev);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));       // the caller's collective runs on another stream

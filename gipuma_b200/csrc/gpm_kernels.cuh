@@ -144,7 +144,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
         const int py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1);
         if (px < W && py < H) {
             const size_t center = (size_t)py * W + px;
-            setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+            bool window_ready = false;          // the per-pixel window data is only built if something gets evaluated
             const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
             float4 norm_now = planes[center];
             float cost_now = cost[center];
@@ -200,6 +200,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
+                if (!window_ready) { setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
                 const float c = eval_plane<true, PACKED>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
@@ -226,6 +227,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 }
             }
             if (refine) {
+                if (!window_ready) { setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
                 const float4 norm_start = norm_now;
                 bool any_accept = false;
                 // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
@@ -305,7 +307,8 @@ __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
              cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
              const unsigned char* __restrict__ prov, float* __restrict__ dispbuf, float4* __restrict__ candbuf,
-             float* __restrict__ canddepth, int colour, int stage, float* __restrict__ xchg)
+             float* __restrict__ canddepth, float4* __restrict__ seen, unsigned short* __restrict__ memo_mask,
+             int colour, int stage, float* __restrict__ xchg)
 {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
@@ -354,12 +357,23 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                 mine_ok = ok;
                 if (mine_ok) mine = planes[(size_t)qy * W + qx];
             }
+            // direction memo of rejected work, as in k_sweep (identical on every rank: it only depends on the shared state)
+            const unsigned short mmask = P.memo ? memo_mask[center] : (unsigned short)0;
+            bool memo_hit = false;
+            if (P.memo && mine_ok && ((mmask >> lane) & 1)) {
+                const float4 old = seen[center * 8 + lane];
+                memo_hit = __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
+                           __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
+            }
+            const unsigned memo_bits = __ballot_sync(GPM_FULL, memo_hit);
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
+            if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
+            if (P.memo && lane == 0 && (unsigned short)(mmask | (cand_mask & 0xffu)) != mmask) memo_mask[center] = (unsigned short)(mmask | (cand_mask & 0xffu));
             for (int k = 0; k < 8; k++) {
                 float4 nbp;
                 nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
                 nbp.z = __shfl_sync(GPM_FULL, mine.z, k);  nbp.w = __shfl_sync(GPM_FULL, mine.w, k);
-                bool skip = !((cand_mask >> k) & 1);
+                bool skip = !((cand_mask >> k) & 1) || ((memo_bits >> k) & 1);
                 if (!skip) {
                     const float d = plane_depth(cam, nbp.x, nbp.y, nbp.z, nbp.w, fpx, fpy);
                     const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
