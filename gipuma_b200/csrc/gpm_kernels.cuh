@@ -173,20 +173,22 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             // accepted later: seen[p][k] holds the last plane offered from direction k; an unchanged neighbour is skipped
             // without evaluation, in every later iteration.  Exact, not a heuristic.
             unsigned short mmask = P.memo ? memo_mask[center] : (unsigned short)0;
-            bool memo_hit = false;
-            if (P.memo && mine_ok && ((mmask >> lane) & 1)) {
-                const float4 old = seen[center * 8 + lane];
-                memo_hit = __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
-                           __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
-            }
-            const unsigned memo_bits = __ballot_sync(GPM_FULL, memo_hit);
+            const bool old_ok = P.memo && lane < 8 && ((mmask >> lane) & 1);
+            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (old_ok) old = seen[center * 8 + lane];
+            const bool memo_hit = old_ok && mine_ok &&
+                                  __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
+                                  __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
             for (int k = 0; k < 8; k++) {
                 if (!((cand_mask >> k) & 1)) continue;
-                if ((memo_bits >> k) & 1) { st.skip++; continue; }
                 float4 nb;
                 nb.x = __shfl_sync(GPM_FULL, mine.x, k);  nb.y = __shfl_sync(GPM_FULL, mine.y, k);
                 nb.z = __shfl_sync(GPM_FULL, mine.z, k);  nb.w = __shfl_sync(GPM_FULL, mine.w, k);
+                // already offered to this pixel before, from ANY direction (the 8 memo entries double as a history)?
+                const bool known = old_ok && __float_as_uint(nb.x) == __float_as_uint(old.x) && __float_as_uint(nb.y) == __float_as_uint(old.y) &&
+                                   __float_as_uint(nb.z) == __float_as_uint(old.z) && __float_as_uint(nb.w) == __float_as_uint(old.w);
+                if (__any_sync(GPM_FULL, known)) { st.skip++; continue; }
                 // spatialPropagation_cu, gipuma.cu:832-874
                 const float disp_before = plane_depth(cam, nb.x, nb.y, nb.z, nb.w, fpx, fpy);
                 const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
