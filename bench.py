@@ -213,11 +213,13 @@ def run_ours(args, rank, world, local):
                 "d2h_bytes_per_step": int(W * H * 20), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": 446.3e6,
+                     "traffic": 449.7e6,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "kernel": "gpm::k_sweep", "avg_launch_ms": avg_launch_ms,
+                     "binding_unit": {"name": "l1tex__data_pipe_tex_wavefronts", "frac_of_peak": 0.950,
+                                      "source": "ncu --set full, profiles/r01_ncu_k_sweep_cfg2_iter2_black.txt (not measured live)"},
                      "algorithmic_bytes_per_launch": algorithmic_bytes_per_sweep_launch(W, H, V),
-                     "note": "this path is bound by the L1TEX data pipe, not HBM: ncu l1tex__data_pipe_tex_wavefronts = 95.3 % of "
+                     "note": "this path is bound by the L1TEX data pipe, not HBM: ncu l1tex__data_pipe_tex_wavefronts = 95.0 % of "
                              "peak for this kernel (profiles/r01_ncu_k_sweep_cfg2_iter2_black.txt); traffic = ncu dram bytes of that launch "
                              "(iteration 2, black; later launches move less)"},
         "work": {"hypotheses_evaluated": stats["hypotheses"], "hypotheses_skipped_exact": stats["skipped"],

@@ -43,6 +43,7 @@ CASES = [
     (2, 64, 96, 6, 2, 11, 3, 0, 5),                   # COMB_ALL
     (2, 64, 96, 6, 2, 11, 3, 3, 5),                   # COMB_GOOD
     (4, 64, 96, 33, 1, 5, 3, 1, 3),                   # 33 views: second view per lane, pin P3 build
+    (5, 64, 96, 64, 1, 5, 3, 1, 8),                   # GPM_MAX_VIEWS = 64 source views
     (3, 96, 96, 8, 1, 25, 3, 1, 11),                  # largest window (six 32-sample rounds)
     (2, 64, 96, 5, 2, 3, 2, 1, 1),                    # smallest window
 ]

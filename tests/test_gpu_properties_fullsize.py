@@ -74,3 +74,13 @@ def test_error_handling():
             ctx.set_params(sc.params)                     # larger than the reference's tile loader supports
     with pytest.raises(api.GipumaError):
         api.Context(64, 64, 65)                           # more than GPM_MAX_VIEWS
+    with pytest.raises(api.GipumaError):
+        api.Context(64, 64, 0)                            # empty view list
+    with pytest.raises(api.GipumaError):
+        api.Context(4, 4, 1)                              # degenerate image
+    with api.Context(sc.cols, sc.rows, 2) as ctx:
+        with pytest.raises(api.GipumaError):
+            ctx.set_num_views(0)
+        ctx.load_scene(S.make_config(1, rows=64, cols=96))
+        ctx.set_num_views(1)                              # fewer views than uploaded is fine
+        ctx.run()
