@@ -101,6 +101,47 @@ def run_reference_view_batch(make_scene: Callable[[int], object], n_reference_vi
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# both axes at once (BASELINE config 5: "view-shard + ref-view batch")
+# ----------------------------------------------------------------------------------------------------------------
+
+def hybrid_layout(world: int, shard: int):
+    """Split `world` ranks into world/shard groups of `shard` consecutive ranks: the groups work on different reference
+    views (batch axis), the ranks inside a group shard the source views of their group's current reference view.
+    Returns (group_of_rank, rank_in_group, members_of_group) lists."""
+    if shard < 1 or world % shard:
+        raise ValueError("world size must be a multiple of the view-shard width")
+    group_of = [r // shard for r in range(world)]
+    rank_in = [r % shard for r in range(world)]
+    members = [list(range(g * shard, (g + 1) * shard)) for g in range(world // shard)]
+    return group_of, rank_in, members
+
+
+def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank: int, world: int, shard: int,
+               device: int = 0, on_result: Optional[Callable] = None) -> List[float]:
+    """Reference views are dealt round-robin to world/shard groups; inside a group the source views are sharded and
+    combined with one all-gather per stage over the group's own communicator.  Returns wall seconds per reference view."""
+    import time
+    import torch
+    import torch.distributed as dist
+    group_of, rank_in, members = hybrid_layout(world, shard)
+    groups = [dist.new_group(ranks=m) if world > 1 else None for m in members]     # every rank creates every group
+    my_group = group_of[rank]
+    times = []
+    for ref in assign_reference_views(n_reference_views, my_group, len(members)):
+        sc = make_scene(ref)
+        runner = ViewShardRunner(sc, rank_in[rank], shard, device=device, group=groups[my_group])
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        n4, c = runner.run()
+        torch.cuda.synchronize(device)
+        times.append(time.perf_counter() - t0)
+        if on_result is not None and rank_in[rank] == 0:
+            on_result(ref, n4, c)
+        runner.close()
+    return times
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # source-view shard
 # ----------------------------------------------------------------------------------------------------------------
 

@@ -56,6 +56,16 @@ def test_merge_matches_reference_combination_single_process():
         assert np.array_equal(merged.view(np.uint32), want.view(np.uint32))
 
 
+def test_hybrid_layout():
+    group_of, rank_in, members = M.hybrid_layout(8, 4)
+    assert group_of == [0, 0, 0, 0, 1, 1, 1, 1] and rank_in == [0, 1, 2, 3, 0, 1, 2, 3] and members == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    assert M.hybrid_layout(4, 1)[2] == [[0], [1], [2], [3]]
+    with pytest.raises(ValueError):
+        M.hybrid_layout(6, 4)
+    # 8 GPUs, 2 groups: reference views 0..4 -> group 0 gets 0,2,4; group 1 gets 1,3
+    assert M.assign_reference_views(5, 0, 2) == [0, 2, 4] and M.assign_reference_views(5, 1, 2) == [1, 3]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
