@@ -73,7 +73,7 @@ struct gpm_ctx {
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
     int opt_cost_variant = 1, opt_packed = 0, opt_memo = 1;
-    int smem_optin = 0;
+    int smem_optin = 0, num_sms = 148;
 };
 
 namespace {
@@ -160,6 +160,10 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
 {
     const size_t smem = block_smem_bytes(P);
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    // at least ~8 waves of blocks over the SMs: split each tile's pixel list into up to 8 slices for small images
+    int split = 1;
+    while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
+    grid.z = split;
     (P.packed ? k_sweep<true> : k_sweep<false>)<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
                                                       c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
@@ -239,6 +243,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
         ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        ok(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
         ok(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));

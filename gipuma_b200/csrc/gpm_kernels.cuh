@@ -136,8 +136,12 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H;
 
-    int idx = warp;                                                  // dynamic distribution of the tile's 512 pixels
-    while (idx < GPM_TILE * GPM_TILE / 2) {
+    // gridDim.z slices of the tile's 512 pixels of this colour (small images: more, smaller work units -> no idle SMs in
+    // the last wave); inside a slice the warps take pixels dynamically
+    const int per_slice = (GPM_TILE * GPM_TILE / 2 + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int idx_end = min(GPM_TILE * GPM_TILE / 2, ((int)blockIdx.z + 1) * per_slice);
+    int idx = (int)blockIdx.z * per_slice + (int)warp;
+    while (idx < idx_end) {
         // pixel of this colour — gipuma.cu:1730-1734 / 1786-1790
         const int tx = idx & 31, ty = idx >> 5;
         const int px = blockIdx.x * GPM_TILE + tx;
@@ -285,7 +289,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 prov[center] = (unsigned char)prov_now;
             }
         }
-        if (lane == 0) idx = atomicAdd(counter, 1);
+        if (lane == 0) idx = (int)blockIdx.z * per_slice + atomicAdd(counter, 1);
         idx = __shfl_sync(GPM_FULL, idx, 0);
     }
     flush_stats(stats, st, lane);
