@@ -128,11 +128,12 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.rng_mode = c->rng_mode;
     P.ref = c->ref;
     P.ref.depthMin = p.depthMin;  P.ref.depthMax = p.depthMax;
-    // warps per block: as many as fit (<= 16), leaving room for >= 2 resident blocks per SM
+    // warps per block: as many as fit (<= 16).  The kernels use 128 registers per thread, so one 16-warp block fills an SM
+    // anyway; shared memory may therefore be spent up to the per-block opt-in limit.
     const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V) * sizeof(float);
     const size_t fixed = ((size_t)fixed_smem_floats(P) + 4) * sizeof(float);
     int nw = GPM_LB_THREADS / 32;
-    const size_t budget = 100 * 1024;
+    const size_t budget = (size_t)c->smem_optin > 16 * 1024 ? (size_t)c->smem_optin - 8 * 1024 : 40 * 1024;
     while (nw > 2 && fixed + nw * per_warp > budget) nw--;
     if (c->opt_nwarps > 0) nw = c->opt_nwarps;
     if (nw > GPM_LB_THREADS / 32) nw = GPM_LB_THREADS / 32;
