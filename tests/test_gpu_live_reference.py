@@ -132,3 +132,17 @@ def test_border_heavy_scene():
     for opts in ({}, {"memo": 0}):
         ls, _, _ = api.runcuda(sc, seed=123, options=opts)
         assert bits_equal(ls.norm4, r_n4) == 0 and bits_equal(ls.c, r_c) == 0
+
+
+def test_baseline_config2_full_size_bit_exact_vs_live_reference():
+    """BASELINE configs[1] as benchmarked: 1600 x 1200, 10 source views, 8 iterations, blocksize 15 — all 9.6 M output
+    floats identical to the reference's."""
+    from gipuma_b200 import api, scene as S
+    sc = S.make_config(2)
+    assert reference_tile_fully_loaded(sc.rows, sc.cols, sc.params.box_hsize)
+    ref = _ref(sc.n_views)
+    r_n4, r_c, printed_s, _ = ref.run(sc)
+    ls, ms, st = api.runcuda(sc)
+    assert bits_equal(ls.norm4, r_n4) == 0
+    assert bits_equal(ls.c, r_c) == 0
+    assert ms / 1e3 < printed_s          # and faster than the reference over the same span
