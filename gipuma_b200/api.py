@@ -63,6 +63,8 @@ def load_library():
     L.gpm_set_params.argtypes = [vp, C.POINTER(GpmParams)]
     L.gpm_set_reference.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(GpmCamera)]
     L.gpm_set_view.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.POINTER(GpmCamera)]
+    L.gpm_set_reference_color.argtypes = L.gpm_set_reference.argtypes
+    L.gpm_set_view_color.argtypes = L.gpm_set_view.argtypes
     L.gpm_set_num_views.argtypes = [vp, C.c_int]
     L.gpm_set_rng.argtypes = [vp, C.c_ulonglong, C.c_int]
     L.gpm_set_state.argtypes = [vp, vp, vp, C.c_int]
@@ -90,7 +92,8 @@ def load_library():
     L.gpm_shard_eval.argtypes = [vp, C.c_int, C.c_int, vp]
     L.gpm_shard_accept.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.gpm_stream.restype = vp
-    for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_num_views",
+    for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_reference_color",
+                 "gpm_set_view_color", "gpm_set_num_views",
                  "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
                  "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option",
                  "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_eval", "gpm_shard_accept",
@@ -169,15 +172,23 @@ class Context:
         p = pack_params(params)
         self._check(self.lib.gpm_set_params(self.h, C.byref(p)))
 
+    @staticmethod
+    def _is_color(img) -> bool:
+        """[H, W, 4] float images take the reference's -color_processing (float4) path; [H, W] the gray one."""
+        shape = getattr(img, "shape", ())
+        return len(shape) == 3 and shape[-1] == 4
+
     def set_reference(self, img, cam, pitch_bytes: int = 0):
         ptr, dev = _ptr(img)
         g = pack_camera(cam)
-        self._check(self.lib.gpm_set_reference(self.h, ptr, pitch_bytes, dev, C.byref(g)))
+        fn = self.lib.gpm_set_reference_color if self._is_color(img) else self.lib.gpm_set_reference
+        self._check(fn(self.h, ptr, pitch_bytes, dev, C.byref(g)))
 
     def set_view(self, v: int, img, cam, pitch_bytes: int = 0):
         ptr, dev = _ptr(img)
         g = pack_camera(cam)
-        self._check(self.lib.gpm_set_view(self.h, v, ptr, pitch_bytes, dev, C.byref(g)))
+        fn = self.lib.gpm_set_view_color if self._is_color(img) else self.lib.gpm_set_view
+        self._check(fn(self.h, v, ptr, pitch_bytes, dev, C.byref(g)))
 
     def set_num_views(self, n: int):
         self._check(self.lib.gpm_set_num_views(self.h, n))

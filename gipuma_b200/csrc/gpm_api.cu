@@ -38,6 +38,7 @@ static int fail(int code, const std::string& msg)
 
 struct gpm_ctx {
     int device = 0, W = 0, H = 0, maxV = 0, V = 0;
+    int color = -1;                  // -1 undecided, 0 float images, 1 float4 (RGB) images — fixed by the first image upload
     gpm_params prm{};
     bool have_params = false, have_ref = false;
     std::vector<char> have_view;
@@ -56,6 +57,10 @@ struct gpm_ctx {
     float* staging = nullptr;        // W*H floats, upload scratch
     cudaArray_t srcArr = nullptr;
     cudaTextureObject_t srcTex = 0;
+    cudaArray_t srcArr4 = nullptr;   // colour mode: layered RGBA32F + padded float4 reference + float4 staging
+    cudaTextureObject_t srcTex4 = 0;
+    float4* refpad4 = nullptr;
+    float4* staging4 = nullptr;
     cudaArray_t gradArr = nullptr;   // layered RG32F: (Gx, Gy) central differences of every source view (packed sampling mode)
     cudaTextureObject_t gradTex = 0;
     float2* gradLin = nullptr;       // W*H staging for one view's gradients
@@ -72,7 +77,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    int opt_cost_variant = 1, opt_packed = 0, opt_memo = 1;
+    int opt_cost_variant = -1, opt_packed = 0, opt_memo = 1;
     int smem_optin = 0, num_sms = 148;
 };
 
@@ -84,7 +89,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
+int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = false)
 {
     if (!c->have_params) return fail(GPM_E_STATE, "gpm_set_params has not been called");
     if (!c->have_ref) return fail(GPM_E_STATE, "gpm_set_reference has not been called");
@@ -120,7 +125,14 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.n_best = p.n_best;  P.cost_comb = p.cost_comb;  P.good_factor = p.good_factor;
     P.prune = c->opt_prune;
     P.dedupe_self = c->opt_dedupe ? 1 : 0;
-    P.cost_variant = init_phase ? 0 : c->opt_cost_variant;
+    // rounding variant of k_cost_eval: at initialisation the reference's binary is y-first for float, x-first for float4;
+    // gpm_cost_eval defaults to the variant of the propagation kernels (x-first for float, y-first for float4)
+    // (option cost_variant 2 = the initialisation form).  For float4 the initialisation kernel additionally folds the
+    // other gradient term into the FMA (grad_variant).
+    const int cv = eval_call ? c->opt_cost_variant : -1;          // the option only steers gpm_cost_eval
+    P.cost_variant = (init_phase || cv == 2) ? (c->color == 1 ? 1 : 0) : (cv >= 0 ? cv : (c->color == 1 ? 0 : 1));
+    P.grad_variant = (c->color == 1 && (init_phase || cv == 2)) ? 1 : 0;
+    P.color = c->color == 1 ? 1 : 0;
     P.memo = c->opt_memo;
     P.packed = c->opt_packed;
     for (int v = 0; v < c->V; v++) if (!c->view_8bit[v]) P.packed = 0;
@@ -130,7 +142,7 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     P.ref.depthMin = p.depthMin;  P.ref.depthMax = p.depthMax;
     // warps per block: as many as fit (<= 16).  The kernels use 128 registers per thread, so one 16-warp block fills an SM
     // anyway; shared memory may therefore be spent up to the per-block opt-in limit.
-    const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V) * sizeof(float);
+    const size_t per_warp = (size_t)warp_scratch_floats(P.ns_pad, P.V, P.color) * sizeof(float);
     const size_t fixed = ((size_t)fixed_smem_floats(P) + 4) * sizeof(float);
     int nw = GPM_LB_THREADS / 32;
     const size_t budget = (size_t)c->smem_optin > 16 * 1024 ? (size_t)c->smem_optin - 8 * 1024 : 40 * 1024;
@@ -138,6 +150,7 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P)
     if (c->opt_nwarps > 0) nw = c->opt_nwarps;
     if (nw > GPM_LB_THREADS / 32) nw = GPM_LB_THREADS / 32;
     P.nwarps = nw;
+    if (P.color) P.packed = 0;
     if (P.packed && c->opt_packed == 1) {
         // auto: the packed mode triples the texture bytes a warp touches per pixel (4 -> 12 B per texel and view); it only
         // pays while the block's working set stays near the L1 (measured: +11 % at cfg 2, -17 % at cfg 3)
@@ -165,7 +178,7 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
     int split = 1;
     while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
     grid.z = split;
-    (P.packed ? k_sweep<true> : k_sweep<false>)<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
+    (P.color ? k_sweep<false, true> : (P.packed ? k_sweep<true, false> : k_sweep<false, false>))<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
                                                       c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -189,6 +202,21 @@ int upload_image(gpm_ctx* c, const float* img, size_t pitch_bytes, int on_device
 }
 
 }  // namespace
+
+static int ensure_color(gpm_ctx* c, int want);
+
+static void set_ref_camera(gpm_ctx* c, const gpm_camera* cam)
+{
+    RefCam& r = c->ref;
+    memcpy(r.K_inv, cam->K_inv, sizeof(r.K_inv));
+    memcpy(r.M_inv, cam->M_inv, sizeof(r.M_inv));
+    memcpy(r.R_orig_inv, cam->R_orig_inv, sizeof(r.R_orig_inv));
+    memcpy(r.P34, cam->P_col34, sizeof(r.P34));
+    memcpy(r.C, cam->C, sizeof(r.C));
+    r.fx = cam->fx;  r.alpha = cam->alpha;  r.K2 = cam->K[2];  r.K5 = cam->K[5];
+    r.f = cam->f;  r.f_cam = cam->f;  r.baseline = cam->baseline;
+    c->have_ref = true;
+}
 
 extern "C" const char* gpm_last_error(void) { return g_err.c_str(); }
 extern "C" const char* gpm_version(void) { return "gipuma_b200 0.1 (sm_100a)"; }
@@ -245,12 +273,15 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         ok(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-        ok(cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_cost_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_cost_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_cost_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
     }
     if (err != cudaSuccess) {
         std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
@@ -268,6 +299,9 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
+    if (c->srcTex4) cudaDestroyTextureObject(c->srcTex4);
+    if (c->srcArr4) cudaFreeArray(c->srcArr4);
+    cudaFree(c->refpad4);  cudaFree(c->staging4);
     if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
     if (c->gradArr) cudaFreeArray(c->gradArr);
     cudaFree(c->gradLin);  cudaFree(c->d_flag);
@@ -324,20 +358,14 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     DeviceGuard g(c->device);
     float* d = nullptr;
     size_t pf = 0;
-    int rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);
+    int rc = ensure_color(c, 0);
+    if (rc) return rc;
+    rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);
     if (rc) return rc;
     dim3 b(32, 8), gr((c->W + 2 * GPM_APRON + 31) / 32, (c->H + 2 * GPM_APRON + 7) / 8);
     k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch);
     CU(cudaGetLastError());
-    RefCam& r = c->ref;
-    memcpy(r.K_inv, cam->K_inv, sizeof(r.K_inv));
-    memcpy(r.M_inv, cam->M_inv, sizeof(r.M_inv));
-    memcpy(r.R_orig_inv, cam->R_orig_inv, sizeof(r.R_orig_inv));
-    memcpy(r.P34, cam->P_col34, sizeof(r.P34));
-    memcpy(r.C, cam->C, sizeof(r.C));
-    r.fx = cam->fx;  r.alpha = cam->alpha;  r.K2 = cam->K[2];  r.K5 = cam->K[5];
-    r.f = cam->f;  r.f_cam = cam->f;  r.baseline = cam->baseline;
-    c->have_ref = true;
+    set_ref_camera(c, cam);
     CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
     CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
@@ -351,7 +379,9 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     DeviceGuard g(c->device);
     float* d = nullptr;
     size_t pf = 0;
-    int rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);      // host images go through the staging buffer
+    int rc = ensure_color(c, 0);
+    if (rc) return rc;
+    rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);          // host images go through the staging buffer
     if (rc) return rc;
     cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
     m.srcPtr = make_cudaPitchedPtr(d, pf * sizeof(float), c->W, c->H);
@@ -398,6 +428,90 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     return GPM_OK;
 }
 
+
+// ---- colour (float4) images: the reference's -color_processing path (T = float4, main.cpp:560-605) -------------
+static int ensure_color(gpm_ctx* c, int want)
+{
+    if (c->color == -1) c->color = want;
+    if (c->color != want) return fail(GPM_E_STATE, "a context holds either float or float4 images, not both");
+    if (want == 1 && !c->srcArr4) {
+        cudaChannelFormatDesc d4 = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+        CU(cudaMalloc3DArray(&c->srcArr4, &d4, make_cudaExtent(c->W, c->H, c->maxV), cudaArrayLayered));
+        cudaResourceDesc res;  memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;  res.res.array.array = c->srcArr4;
+        cudaTextureDesc td;  memset(&td, 0, sizeof(td));
+        td.addressMode[0] = cudaAddressModeWrap;  td.addressMode[1] = cudaAddressModeWrap;  td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
+        CU(cudaCreateTextureObject(&c->srcTex4, &res, &td, NULL));
+        CU(cudaMalloc(&c->refpad4, (size_t)c->refpitch * (c->H + 2 * GPM_APRON) * sizeof(float4)));
+        CU(cudaMalloc(&c->staging4, (size_t)c->W * c->H * sizeof(float4)));
+    }
+    return GPM_OK;
+}
+
+static int upload_image4(gpm_ctx* c, const float* img, size_t pitch_bytes, int on_device, float4** dev_img, size_t* dev_pitch_elems)
+{
+    if (pitch_bytes == 0) pitch_bytes = (size_t)c->W * sizeof(float4);
+    if (pitch_bytes % sizeof(float4)) return fail(GPM_E_ARG, "pitch_bytes must be a multiple of 16 for float4 images");
+    if (on_device) { *dev_img = (float4*)img;  *dev_pitch_elems = pitch_bytes / sizeof(float4);  return GPM_OK; }
+    CU(cudaMemcpy2DAsync(c->staging4, (size_t)c->W * sizeof(float4), img, pitch_bytes, (size_t)c->W * sizeof(float4), c->H,
+                         cudaMemcpyHostToDevice, c->stream));
+    *dev_img = c->staging4;
+    *dev_pitch_elems = c->W;
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_reference_color(gpm_ctx* c, const float* rgba, size_t pitch_bytes, int on_device, const gpm_camera* cam)
+{
+    if (!c || !rgba || !cam) return fail(GPM_E_ARG, "gpm_set_reference_color: null argument");
+    DeviceGuard g(c->device);
+    int rc = ensure_color(c, 1);
+    if (rc) return rc;
+    float4* d = nullptr;
+    size_t pe = 0;
+    rc = upload_image4(c, rgba, pitch_bytes, on_device, &d, &pe);
+    if (rc) return rc;
+    dim3 b(32, 8), gr((c->W + 2 * GPM_APRON + 31) / 32, (c->H + 2 * GPM_APRON + 7) / 8);
+    k_pad_reference4<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->refpad4, c->refpitch);
+    CU(cudaGetLastError());
+    set_ref_camera(c, cam);
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_set_view_color(gpm_ctx* c, int v, const float* rgba, size_t pitch_bytes, int on_device, const gpm_camera* cam)
+{
+    if (!c || !rgba || !cam) return fail(GPM_E_ARG, "gpm_set_view_color: null argument");
+    if (v < 0 || v >= c->maxV) return fail(GPM_E_ARG, "gpm_set_view_color: view index out of range");
+    DeviceGuard g(c->device);
+    int rc = ensure_color(c, 1);
+    if (rc) return rc;
+    float4* d = nullptr;
+    size_t pe = 0;
+    rc = upload_image4(c, rgba, pitch_bytes, on_device, &d, &pe);
+    if (rc) return rc;
+    cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
+    m.srcPtr = make_cudaPitchedPtr(d, pe * sizeof(float4), c->W, c->H);
+    m.dstArray = c->srcArr4;
+    m.dstPos = make_cudaPos(0, 0, v);
+    m.extent = make_cudaExtent(c->W, c->H, 1);
+    m.kind = cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpy3DAsync(&m, c->stream));
+    ViewCam& vc = c->h_cams[v];
+    memcpy(vc.K, cam->K, sizeof(vc.K));
+    memcpy(vc.R, cam->R, sizeof(vc.R));
+    memcpy(vc.t, cam->t, sizeof(vc.t));
+    c->cams_dirty = true;
+    c->have_view[v] = 1;
+    c->view_8bit[v] = 0;
+    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
 extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, int on_device)
 {
     if (!c) return fail(GPM_E_ARG, "gpm_set_state: null context");
@@ -408,7 +522,7 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
     // provenance of the supplied costs is unknown (2) unless the caller vouches that they came from an
     // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
-    CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? 0 : 2, n, c->stream));
+    CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? (c->color == 1 ? 1 : 0) : 2, n, c->stream));
     CU(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned short), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
@@ -438,11 +552,11 @@ static int do_init(gpm_ctx* c)
     c->launches++;
     CU(cudaGetLastError());
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    (P.packed ? k_cost_eval<true> : k_cost_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes,
+    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes,
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(c->prov, 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation
+    CU(cudaMemsetAsync(c->prov, c->color == 1 ? 1 : 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation
     CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
     return GPM_OK;
 }
@@ -527,7 +641,7 @@ extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, i
     if (!c || !planes || !out_cost) return fail(GPM_E_ARG, "gpm_cost_eval: null argument");
     DeviceGuard g(c->device);
     KParams P;
-    int rc = build_kparams(c, false, P);
+    int rc = build_kparams(c, false, P, true);
     if (rc) return rc;
     rc = sync_cams(c);
     if (rc) return rc;
@@ -541,7 +655,7 @@ extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, i
         CU(cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     }
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    (P.packed ? k_cost_eval<true> : k_cost_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, d_pl, d_out, nullptr);
+    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, d_pl, d_out, nullptr);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !on_device) e = cudaMemcpyAsync(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
@@ -622,7 +736,7 @@ extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev
     int rc = shard_common(c, stage, P);
     if (rc) return rc;
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    (P.packed ? k_shard_eval<true> : k_shard_eval<false>)<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, c->refpad, c->srcTex, c->gradTex, c->planes, c->cost,
+    (P.color ? k_shard_eval<false, true> : (P.packed ? k_shard_eval<true, false> : k_shard_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost,
                                                                           c->prov, c->dispbuf, c->candbuf, c->canddepth, c->seen, c->memo_mask, colour, stage, xchg_dev);
     c->launches++;
     CU(cudaGetLastError());
@@ -690,7 +804,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "trust_state") c->opt_trust_state = value != 0;
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
-    else if (n == "cost_variant") c->opt_cost_variant = value != 0;
+    else if (n == "cost_variant") c->opt_cost_variant = value < 0 ? -1 : (value > 2 ? 1 : value);
     else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");

@@ -13,10 +13,19 @@ __device__ __forceinline__ void stage_block(const KParams& P, const float* __res
                                             int tile_x0, int tile_y0)
 {
     const int tw = P.tile_w;
+    if (P.color) {                                  // float4 texels: refpitch counts float4 elements
+        const float4* src4 = reinterpret_cast<const float4*>(refpad) + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
+        float4* tile4 = reinterpret_cast<float4*>(tile);
+        for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
+            const int J = e / tw, I = e - J * tw;
+            tile4[e] = src4[(size_t)J * P.refpitch + I];
+        }
+    } else {
     const float* src = refpad + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
     for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
         const int J = e / tw, I = e - J * tw;
         tile[e] = src[(size_t)J * P.refpitch + I];
+    }
     }
     const float* c = reinterpret_cast<const float*>(cams);
     for (int e = threadIdx.x; e < P.V * GPM_VIEWCAM_FLOATS; e += blockDim.x) sCam[e] = c[e];
@@ -34,10 +43,11 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const War
 }
 
 // shared memory: [tile tw*tw][cams V*21][pad to 16 B][nwarps * warp_scratch][1 int work counter]
-__host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (P.tile_w * P.tile_w + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
+__host__ __device__ inline int tile_floats(const KParams& P) { return P.tile_w * P.tile_w * (P.color ? 4 : 1); }
+__host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (tile_floats(P) + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
 __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
 {
-    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V) + 4;
+    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4;
     return fl * sizeof(float);
 }
 
@@ -81,7 +91,7 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
 #define GPM_LB_THREADS 512       // max threads per block of the warp-per-pixel kernels (16 warps)
 #define GPM_LB_BLOCKS 1
 #endif
-template <bool PACKED>
+template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
             cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, float* __restrict__ cost,
@@ -89,22 +99,22 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
-    float* sCam = tile + P.tile_w * P.tile_w;
+    float* sCam = tile + tile_floats(P);
     float* scratch = smem + fixed_smem_floats(P);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
     WarpStats st = {0, 0, 0, 0, 0};
     for (int idx = warp; idx < GPM_TILE * GPM_TILE; idx += P.nwarps) {
         const int px = blockIdx.x * GPM_TILE + (idx & 31), py = blockIdx.y * GPM_TILE + (idx >> 5);
         if (px >= P.W || py >= P.H) continue;
-        setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
         const float inf = __int_as_float(0x7f800000);
-        const float c = P.cost_variant ? eval_plane<true, PACKED>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
-                                       : eval_plane<false, PACKED>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
+        const float c = P.cost_variant ? eval_plane<true, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
+                                       : eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
         if (lane == 0) cost[(size_t)py * P.W + px] = c;
     }
     flush_stats(stats, st, lane);
@@ -113,7 +123,7 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 // ---- one checkerboard colour: close + far propagation + refinement, fused --------------------
 // gipuma_{black,red}_spatialPropClose_cu / spatialPropFar_cu / planeRefine_cu, gipuma.cu:1353-1823.
 // colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
-template <bool PACKED>
+template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
@@ -123,15 +133,15 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
 {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
-    float* sCam = tile + P.tile_w * P.tile_w;
+    float* sCam = tile + tile_floats(P);
     float* scratch = smem + fixed_smem_floats(P);
-    int* counter = reinterpret_cast<int*>(scratch + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V));
+    int* counter = reinterpret_cast<int*>(scratch + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color));
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     if (threadIdx.x == 0) *counter = P.nwarps;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H;
@@ -153,7 +163,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             float4 norm_now = planes[center];
             float cost_now = cost[center];
             float disp_now = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);   // :1530
-            // which rounding variant of the cost function produced cost_now: 0 = init/refine, 1 = propagation, 2 = unknown
+            // which rounding variant of the cost function produced cost_now: 0 = y-first (XFIRST false), 1 = x-first, 2 = unknown
             int prov_now = prov[center];
 
             // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462)
@@ -198,7 +208,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
                 // exact duplicates: cost(p, plane) is a pure function, so a plane equal to the current one or to an
                 // earlier candidate of this pixel cannot be accepted (`cost_before < *cost_now` is false)
-                const bool same_now = P.dedupe_self && prov_now == 1 &&
+                const bool same_now = P.dedupe_self && prov_now == (COLOR ? 0 : 1) &&
                                       __float_as_uint(nb.x) == __float_as_uint(norm_now.x) && __float_as_uint(nb.y) == __float_as_uint(norm_now.y) &&
                                       __float_as_uint(nb.z) == __float_as_uint(norm_now.z) && __float_as_uint(nb.w) == __float_as_uint(norm_now.w);
                 const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
@@ -206,13 +216,14 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
-                if (!window_ready) { setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
-                const float c = eval_plane<true, PACKED>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+                // rounding variant of the propagation kernels: x-first for float images, y-first for float4
+                const float c = eval_plane<!COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
                     norm_now = nb;
                     cost_now = c;
-                    prov_now = 1;
+                    prov_now = COLOR ? 0 : 1;
                 }
             }
 
@@ -233,7 +244,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 }
             }
             if (refine) {
-                if (!window_ready) { setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+                if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
                 const float4 norm_start = norm_now;
                 bool any_accept = false;
                 // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
@@ -263,7 +274,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
                     if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
                     cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
-                    const float c = eval_plane<false, PACKED>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    const float c = eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
                     if (c < cost_now) {                                                          // :986-990 (no depth-range test)
                         prov_now = 0;
                         any_accept = true;
@@ -308,7 +319,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
 //   stage 2 + s    refinement step s                         (1 slot; sequential: step s+1 depends on step s' accept)
 // Exchange index of pixel (x, y): y * ceil(W/2) + x/2 (pixels of one colour have distinct x/2 within a row).
 // ============================================================================================================
-template <bool PACKED>
+template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
              cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
@@ -318,13 +329,13 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
 {
     extern __shared__ __align__(16) float smem[];
     float* tile = smem;
-    float* sCam = tile + P.tile_w * P.tile_w;
+    float* sCam = tile + tile_floats(P);
     float* scratch = smem + fixed_smem_floats(P);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V), P.ns_pad, P.V);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
@@ -340,12 +351,12 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
         const size_t center = (size_t)py * W + px;
         // stage 0 exchanges both colours: two half-resolution planes back to back
         float* out = xchg + (((stage == 0 ? (size_t)((px + py) & 1) * H * Wh : 0) + (size_t)py * Wh + (px >> 1)) * slots) * nb;
-        setup_window(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
         const float4 norm_now = planes[center];
         float c0, c1;
         if (stage == 0) {
-            eval_plane<false, PACKED>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
+            eval_plane<COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);   // init variant
             local_topn(P, c0, c1, lane, out);
         } else if (stage == 1) {
             const int prov_now = prov[center];
@@ -392,7 +403,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                     (void)prov_now;
                 }
                 if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-                eval_plane<true, PACKED>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+                eval_plane<!COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
                 local_topn(P, c0, c1, lane, out + k * nb);
             }
         } else {
@@ -422,7 +433,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
             if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
             cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
             if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
-            eval_plane<false, PACKED>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         }
     }
@@ -470,7 +481,7 @@ __global__ void k_shard_accept(const __grid_constant__ KParams P, float4* __rest
         const float* g = gathered + (((stage == 0 ? (size_t)col * H * Wh : 0) + (size_t)py * Wh + hx) * slots) * nb;
         if (stage == 0) {
             cost[center] = shard_merge(g, per_rank, world, nb);
-            prov[center] = 0;
+            prov[center] = P.color ? 1 : 0;          // initialisation variant
         } else if (stage == 1) {
             float4 norm_now = planes[center];
             float cost_now = cost[center];
@@ -485,7 +496,7 @@ __global__ void k_shard_accept(const __grid_constant__ KParams P, float4* __rest
                     norm_now = planes[(size_t)qy * W + qx];                 // other colour: not written by this launch
                     disp_now = plane_depth(P.ref, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
                     cost_now = c;
-                    prov_now = 1;
+                    prov_now = P.color ? 0 : 1;
                 }
             }
             planes[center] = norm_now;  cost[center] = cost_now;  dispbuf[center] = disp_now;  prov[center] = (unsigned char)prov_now;
@@ -527,6 +538,14 @@ __global__ void k_make_gradients(const float* __restrict__ img, size_t pitch_flo
     const float gy = fsub(img[(size_t)min(y + 1, H - 1) * pitch_floats + x], img[(size_t)max(y - 1, 0) * pitch_floats + x]);
     out[(size_t)y * W + x] = make_float2(gx, gy);
     if (!(v >= 0.0f && v <= 255.0f && v == rintf(v))) *all_8bit = 0;
+}
+
+__global__ void k_pad_reference4(const float4* __restrict__ img, size_t pitch_elems, int W, int H, float4* __restrict__ out, int out_pitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W + 2 * GPM_APRON || y >= H + 2 * GPM_APRON) return;
+    const int sx = min(max(x - GPM_APRON, 0), W - 1), sy = min(max(y - GPM_APRON, 0), H - 1);
+    out[(size_t)y * out_pitch + x] = img[(size_t)sy * pitch_elems + sx];
 }
 
 // replicate-pad the reference image by GPM_APRON on every side (== the texture's clamp addressing, main.cpp:644-645)

@@ -7,7 +7,8 @@
 //   gs.params                     -> gpm_params                 (fields read on device, algorithmparameters.h:53-84)
 //   gs.cameras->cameras[0]        -> gpm_set_reference camera   (K_inv, M_inv, P_col34, C4, fx, alpha, K, f, baseline, R_orig_inv)
 //   gs.cameras->cameras[subset[v]]-> gpm_set_view camera        (K, R, t4)
-//   gs.cuArray[i]                 -> linear device copy of the float image (the texture objects gs.imgs[] are not used)
+//   gs.cuArray[i]                 -> linear device copy of the float (or, with -color_processing, float4) image
+//                                    (the texture objects gs.imgs[] are not used)
 //   gs.lines->norm4 / c           <- gpm_get_state (managed memory, visible to the host on return: main.cpp:976-985)
 // Behaviour kept from the reference: synchronous, returns 0, prints the same progress lines, CUDA/argument
 // failures print a message and exit(EXIT_FAILURE) like checkCudaErrors (helper_cuda.h:890-905).
@@ -60,10 +61,8 @@ int runcuda(GlobalState& gs)
     const AlgorithmParameters& a = *gs.params;
     CameraParameters_cu& cpc = *gs.cameras;
     const int rows = cpc.rows, cols = cpc.cols, V = cpc.viewSelectionSubsetNumber;
-    if (a.color_processing) {
-        fprintf(stderr, "gipuma_b200 runcuda: -color_processing (float4 images) is not implemented; use grayscale\n");
-        exit(EXIT_FAILURE);
-    }
+    const bool col = a.color_processing;                      // T = float4 (gipuma.cu:1965-1966)
+    const size_t texel = col ? 4 * sizeof(float) : sizeof(float);
     int device = 0;
     cudaGetDevice(&device);                                   // main.cpp:690 selected it already
     gpm_ctx* ctx = nullptr;
@@ -80,19 +79,21 @@ int runcuda(GlobalState& gs)
     GPM_CHECK(gpm_set_params(ctx, &p));
 
     float* lin = nullptr;
-    if (cudaMalloc(&lin, (size_t)rows * cols * sizeof(float)) != cudaSuccess) die("cudaMalloc", -2);
+    if (cudaMalloc(&lin, (size_t)rows * cols * texel) != cudaSuccess) die("cudaMalloc", -2);
     gpm_camera cam;
     fill_camera(cam, cpc.cameras[REFERENCE]);
     cam.f = cpc.f;                                            // gipuma.cu:904 reads camParams.f; == cameras[0].f (cameraGeometryUtils.h:315-316)
-    if (cudaMemcpy2DFromArray(lin, cols * sizeof(float), gs.cuArray[REFERENCE], 0, 0, cols * sizeof(float), rows,
+    if (cudaMemcpy2DFromArray(lin, cols * texel, gs.cuArray[REFERENCE], 0, 0, cols * texel, rows,
                               cudaMemcpyDeviceToDevice) != cudaSuccess) die("cudaMemcpy2DFromArray", -2);
-    GPM_CHECK(gpm_set_reference(ctx, lin, 0, 1, &cam));
+    if (col) GPM_CHECK(gpm_set_reference_color(ctx, lin, 0, 1, &cam));
+    else GPM_CHECK(gpm_set_reference(ctx, lin, 0, 1, &cam));
     for (int v = 0; v < V; v++) {
         const int idx = cpc.viewSelectionSubset[v];           // gipuma.cu:743
         fill_camera(cam, cpc.cameras[idx]);
-        if (cudaMemcpy2DFromArray(lin, cols * sizeof(float), gs.cuArray[idx], 0, 0, cols * sizeof(float), rows,
+        if (cudaMemcpy2DFromArray(lin, cols * texel, gs.cuArray[idx], 0, 0, cols * texel, rows,
                                   cudaMemcpyDeviceToDevice) != cudaSuccess) die("cudaMemcpy2DFromArray", -2);
-        GPM_CHECK(gpm_set_view(ctx, v, lin, 0, 1, &cam));
+        if (col) GPM_CHECK(gpm_set_view_color(ctx, v, lin, 0, 1, &cam));
+        else GPM_CHECK(gpm_set_view(ctx, v, lin, 0, 1, &cam));
         cudaDeviceSynchronize();                              // `lin` is reused for the next view
     }
     GPM_CHECK(gpm_set_num_views(ctx, V));

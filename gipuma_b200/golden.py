@@ -32,5 +32,6 @@ def scene_from_arrays(name: str, z) -> Scene:
         kw = {m: np.ascontiguousarray(z["cam_" + m][i], dtype=np.float32) for m in _CAM_MATS}
         sc = {s: float(z["cam_scalars"][i, k]) for k, s in enumerate(_CAM_SCALARS)}
         cams.append(Camera(**kw, **sc))
+    p.color_processing = z["images_u8"].ndim == 4          # [n, rows, cols, 4]: the float4 path
     return Scene(name=name, rows=int(z["rows"]), cols=int(z["cols"]), images=z["images_u8"].astype(np.float32),
                  cameras=cams, subset=[int(v) for v in z["subset"]], params=p)

@@ -16,6 +16,7 @@ Host-side input preparation only (NumPy); nothing here is on the timed path.
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 from dataclasses import dataclass, field, asdict
 from typing import List, Optional, Sequence
@@ -332,6 +333,20 @@ def render_scene(name: str, Ps: Sequence[np.ndarray], rows: int, cols: int, para
     params.max_disparity = float(f * b / np.float32(params.depthMin))     # main.cpp:906
     return Scene(name=name, rows=rows, cols=cols, images=images, cameras=cams, subset=subset, params=params,
                  gt_depth=gt, meta={"z0": z0, "seed": seed, "cam_scale": cam_scale})
+
+
+def colorize(scene: Scene) -> Scene:
+    """The same scene with float4 images [n, rows, cols, 4] and color_processing on (the reference converts the
+    8-bit BGR image to 4 float channels, main.cpp:560-605 / 1080-1110; the 4th channel is never read by the float4
+    operators, vector_operations.h:3-38).  Each channel is a fixed function of the rendered gray value, so the views
+    stay photo-consistent; values are integers in [0, 255] like a decoded 8-bit image."""
+    g = scene.images.astype(np.float64)
+    b = g
+    gr = np.clip(np.rint(245.0 - 0.85 * g), 0, 255)
+    r = np.clip(np.rint(127.5 + 110.0 * np.sin(g / 23.0)), 0, 255)
+    images = np.stack([b, gr, r, np.zeros_like(g)], axis=-1).astype(np.float32)
+    params = dataclasses.replace(scene.params, color_processing=True)
+    return dataclasses.replace(scene, name=scene.name + "_color", images=np.ascontiguousarray(images), params=params)
 
 
 # ----------------------------------------------------------------------------------------------

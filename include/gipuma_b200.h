@@ -79,6 +79,12 @@ int gpm_set_reference(gpm_ctx* ctx, const float* img, size_t pitch_bytes, int on
 /* Source view `v` (0-based position in viewSelectionSubset, main.cpp:888-892). */
 int gpm_set_view(gpm_ctx* ctx, int v, const float* img, size_t pitch_bytes, int on_device, const gpm_camera* cam);
 
+/* Colour images: the reference's -color_processing path (T = float4, gipuma.cu:1965-1966; images built at
+ * main.cpp:560-605).  `rgba` is row-major float4 per pixel (x, y, z = the three colour channels, w ignored — the
+ * reference's float4 operators drop it, vector_operations.h:3-38).  A context holds either float or float4 images. */
+int gpm_set_reference_color(gpm_ctx* ctx, const float* rgba, size_t pitch_bytes, int on_device, const gpm_camera* cam);
+int gpm_set_view_color(gpm_ctx* ctx, int v, const float* rgba, size_t pitch_bytes, int on_device, const gpm_camera* cam);
+
 /* Number of source views actually used (viewSelectionSubsetNumber, main.cpp:918). */
 int gpm_set_num_views(gpm_ctx* ctx, int n_views);
 
@@ -140,8 +146,9 @@ int gpm_reset_stats(gpm_ctx* ctx);
  * "prune" (1): exact lower-bound early-out; "dedupe" (1): skip bit-identical candidate planes;
  * "trust_state" (0): treat a state loaded with gpm_set_state as cost-consistent; "nwarps" (0 = auto): warps per block;
  * "stats" (1): maintain the gpm_get_stats counters; "memo" (1): skip candidates / refinements this pixel is already
- * known to reject (exact); "cost_variant" (1): rounding variant used by gpm_cost_eval (1 = propagation kernels, 0 = init /
- * refinement kernels).
+ * known to reject (exact); "cost_variant" (-1 = auto): which of the reference binary's rounding variants gpm_cost_eval
+ * reproduces: 1 = x-term first (float: propagation kernels), 0 = y-term first (float: init / refinement; float4:
+ * all six sweep kernels), 2 = the initialisation kernel's form; auto = the propagation kernels' form.
  * EXPERIMENTAL, not covered by the bit-exactness statement: "packed" (0 = off, 1 = auto, 2 = on) samples the source-view
  * gradients with one RG32F fetch instead of four R32F fetches for 8-bit images; measured 1 differing pixel in 1.92 M at cfg 2. */
 int gpm_set_option(gpm_ctx* ctx, const char* name, int value);

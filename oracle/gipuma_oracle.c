@@ -32,9 +32,15 @@ typedef struct gpo_scene {
     const gpm_params* prm;
     const gpm_camera* ref;    /* cameras[REFERENCE] */
     const gpm_camera* views;  /* [V] cameras[viewSelectionSubset[v]] */
-    const float* ref_img;     /* H*W */
-    const float* const* view_imgs; /* [V] H*W each */
+    const float* ref_img;     /* H*W (gray) or H*W*4 interleaved (colour) */
+    const float* const* view_imgs; /* [V], same layout each */
+    int color;                /* params.color_processing: T = float4 (gipuma.cu:1965-1966) */
 } gpo_scene;
+
+/* Colour mode of the entry points below (off by default).  The images then hold 4 interleaved floats per pixel, the
+ * 4th unused, as main.cpp:560-605 uploads them. */
+static int g_color = 0;
+void gpo_set_color(int on) { g_color = on != 0; }
 
 /* ---- texture unit model: tex2D<float>(tex, x, y), Linear filter, clamp, unnormalised (main.cpp:642-648) ---- */
 static float texel(const float* img, int W, int H, int i, int j)
@@ -56,6 +62,39 @@ static float tex2d(const float* img, int W, int H, float x, float y)
     const float t00 = texel(img, W, H, i, j), t10 = texel(img, W, H, i + 1, j);
     const float t01 = texel(img, W, H, i, j + 1), t11 = texel(img, W, H, i + 1, j + 1);
     return (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+}
+
+/* float4 texture: the same filter per channel (one set of weights) */
+static float texel_c(const float* img, int W, int H, int i, int j, int ch)
+{
+    if (i < 0) i = 0; else if (i >= W) i = W - 1;
+    if (j < 0) j = 0; else if (j >= H) j = H - 1;
+    return img[((size_t)j * W + i) * 4 + ch];
+}
+static void texel3(const float* img, int W, int H, int i, int j, float out[3])
+{
+    for (int ch = 0; ch < 3; ch++) out[ch] = texel_c(img, W, H, i, j, ch);
+}
+static void tex2d3(const float* img, int W, int H, float x, float y, float out[3])
+{
+    if (!(x == x) || !(y == y)) { texel3(img, W, H, 0, 0, out); return; }
+    float xb = x - 0.5f, yb = y - 0.5f;
+    if (xb < -4.0f) xb = -4.0f; else if (xb > (float)W + 4.0f) xb = (float)W + 4.0f;
+    if (yb < -4.0f) yb = -4.0f; else if (yb > (float)H + 4.0f) yb = (float)H + 4.0f;
+    const float fi = floorf(xb), fj = floorf(yb);
+    const float a = floorf((xb - fi) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const float b = floorf((yb - fj) * 256.0f + 0.5f) * (1.0f / 256.0f);
+    const int i = (int)fi, j = (int)fj;
+    for (int ch = 0; ch < 3; ch++) {
+        const float t00 = texel_c(img, W, H, i, j, ch), t10 = texel_c(img, W, H, i + 1, j, ch);
+        const float t01 = texel_c(img, W, H, i, j + 1, ch), t11 = texel_c(img, W, H, i + 1, j + 1, ch);
+        out[ch] = (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+    }
+}
+/* l1_norm(float4), gipuma.cu:173-178: the 4th channel does not take part */
+static float l1_norm3(const float a[3], const float b[3])
+{
+    return (fabsf(a[0] - b[0]) + fabsf(a[1] - b[1]) + fabsf(a[2] - b[2])) * 0.3333333f;
 }
 
 /* ---- geometry ---------------------------------------------------------------------------------------- */
@@ -132,6 +171,44 @@ static float view_cost(const gpo_scene* s, int v, int px, int py, const float n[
     return cost;
 }
 
+/* The same with T = float4: every image difference becomes l1_norm(float4) (gipuma.cu:173-178), i.e. the mean absolute
+ * difference of the three colour channels; gradients are per-channel differences (:251-252, :258-259). */
+static float view_cost_color(const gpo_scene* s, int v, int px, int py, const float n[4], int rad)
+{
+    const gpm_params* p = s->prm;
+    float H[9];
+    homography(s->ref, &s->views[v], n, H);
+    const float* L = s->ref_img;
+    const float* R = s->view_imgs[v];
+    const int W = s->W, Hh = s->H;
+    float center[3];
+    texel3(L, W, Hh, px, py, center);
+    float cost = 0.0f;
+    for (int i = -rad; i < rad + 1; i += 2) {
+        for (int j = -rad; j < rad + 1; j += 2) {
+            const int x = px + i, y = py + j;
+            float left[3], a[3], b[3], c[3], d[3], gx1[3], gy1[3], gx2[3], gy2[3], right[3];
+            texel3(L, W, Hh, x, y, left);
+            const float w = expf(-l1_norm3(left, center) / p->gamma);                     /* weight_cu<float4> :186-190 */
+            const float fx = (float)x, fy = (float)y;
+            const float X = H[0] * fx + H[1] * fy + H[2], Y = H[3] * fx + H[4] * fy + H[5], Z = H[6] * fx + H[7] * fy + H[8];
+            const float qx = X / Z, qy = Y / Z;
+            tex2d3(R, W, Hh, qx + 1 + 0.5f, qy + 0.5f, a);  tex2d3(R, W, Hh, qx - 1 + 0.5f, qy + 0.5f, b);
+            tex2d3(R, W, Hh, qx + 0.5f, qy + 1 + 0.5f, c);  tex2d3(R, W, Hh, qx + 0.5f, qy - 1 + 0.5f, d);
+            tex2d3(R, W, Hh, qx + 0.5f, qy + 0.5f, right);
+            for (int k = 0; k < 3; k++) { gx2[k] = a[k] - b[k];  gy2[k] = c[k] - d[k]; }
+            texel3(L, W, Hh, x + 1, y, a);  texel3(L, W, Hh, x - 1, y, b);
+            texel3(L, W, Hh, x, y + 1, c);  texel3(L, W, Hh, x, y - 1, d);
+            for (int k = 0; k < 3; k++) { gx1[k] = a[k] - b[k];  gy1[k] = c[k] - d[k]; }
+            const float colDiff = l1_norm3(left, right);                                                   /* :253 */
+            const float gradDis = fminf((l1_norm3(gx1, gx2) + l1_norm3(gy1, gy2)) * 0.0625f, p->tau_gradient);   /* :267 */
+            const float colDis = fminf(colDiff, p->tau_color);
+            cost = cost + w * ((1.f - p->alpha) * colDis + p->alpha * gradDis);
+        }
+    }
+    return cost;
+}
+
 /* sort_small, gipuma.cu:684-693 */
 static void sort_small(float* d, int n)
 {
@@ -150,7 +227,7 @@ static float multiview_cost(const gpo_scene* s, int px, int py, const float n[4]
     float cv[GPM_MAX_VIEWS];
     int numValid = 0;
     for (int v = 0; v < s->V; v++) {
-        float c = view_cost(s, v, px, py, n, rad);
+        float c = s->color ? view_cost_color(s, v, px, py, n, rad) : view_cost(s, v, px, py, n, rad);
         if (c < MAXCOST) numValid++; else c = MAXCOST;                  /* :771-774 */
         cv[v] = c;
     }
@@ -210,6 +287,7 @@ static void make_scene(gpo_scene* s, int W, int H, int V, const gpm_params* prm,
                        const gpm_camera* views, const float* ref_img, const float* const* view_imgs)
 {
     s->W = W; s->H = H; s->V = V; s->prm = prm; s->ref = ref; s->views = views; s->ref_img = ref_img; s->view_imgs = view_imgs;
+    s->color = g_color;
 }
 
 /* Cost of the given planes at the pixels of rows [y0, y1) (all columns).  init_radius != 0 uses box/2

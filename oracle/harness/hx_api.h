@@ -24,7 +24,7 @@ typedef struct hx_params {
     int   iterations;                    /* :31 */
     int   n_best, cost_comb;             /* :41-42 */
     float good_factor;                   /* :40 */
-    int   color_processing;              /* :32 (0 only; float4 path not driven) */
+    int   color_processing;              /* :32; 1: images are n_images x rows x cols x 4 floats (B, G, R, unused) */
     float depthMin, depthMax;            /* main.cpp:898-903 -> cameras[0].depthMin/Max */
 } hx_params;
 

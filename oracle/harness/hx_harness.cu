@@ -113,11 +113,13 @@ int build_scene(Scene& sc, const hx_params* p, int rows, int cols, int n_images,
     gs->lines->s = cols;
     gs->lines->l = cols;
 
+    const int ch = p->color_processing ? 4 : 1;   /* float4 images: addImageToTextureFloatColor, main.cpp:560-605 */
     for (int i = 0; i < n_images; i++) {          /* main.cpp:607-656 */
-        cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        cudaChannelFormatDesc desc = p->color_processing ? cudaCreateChannelDesc<float4>()
+                                                         : cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         checkCudaErrors(cudaMallocArray(&gs->cuArray[i], &desc, cols, rows));
-        checkCudaErrors(cudaMemcpy2DToArray(gs->cuArray[i], 0, 0, images + (size_t)i * rows * cols,
-                                            cols * sizeof(float), cols * sizeof(float), rows,
+        checkCudaErrors(cudaMemcpy2DToArray(gs->cuArray[i], 0, 0, images + (size_t)i * rows * cols * ch,
+                                            cols * sizeof(float) * ch, cols * sizeof(float) * ch, rows,
                                             cudaMemcpyHostToDevice));
         cudaResourceDesc res;  memset(&res, 0, sizeof(res));
         res.resType = cudaResourceTypeArray;  res.res.array.array = gs->cuArray[i];
@@ -235,22 +237,24 @@ void ref_setup_tiles(GlobalState& gs, dim3& grid, dim3& block, dim3& grid16, dim
 /* Cost of a given plane at every pixel through the reference's own iteration-time device
  * function (pmCostMultiview_cu with the shared tile).  The kernel body around the call is
  * ours: whole tile loaded by all threads before anyone leaves. */
+template <typename T>
 __global__ void hx_cost_eval_kernel(GlobalState& gs, const float4* planes, float* out, int color)
 {
-    extern __shared__ float hx_tile[];
+    extern __shared__ __align__(16) unsigned char hx_smem[];
+    T* hx_tile = reinterpret_cast<T*>(hx_smem);
     const int rows = gs.cameras->rows, cols = gs.cameras->cols;
     int2 p = make_int2(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
     p.y = p.y * 2 + (((threadIdx.x & 1) != 0) ^ (color != 0) ? 1 : 0);
     int2 tile_offset = make_int2(blockIdx.x * 32 - WIN_RADIUS_W, blockIdx.y * 32 - WIN_RADIUS_H);
     for (int e = threadIdx.y * 32 + threadIdx.x; e < SHARED_SIZE; e += 512) {
         int I = e % SHARED_SIZE_W, J = e / SHARED_SIZE_W;
-        hx_tile[e] = tex2D<float>(gs.imgs[REFERENCE], tile_offset.x + I + 0.5f, tile_offset.y + J + 0.5f);
+        hx_tile[e] = tex2D<T>(gs.imgs[REFERENCE], tile_offset.x + I + 0.5f, tile_offset.y + J + 0.5f);
     }
     __syncthreads();
     if (p.x >= cols || p.y >= rows) return;
     int box_hrad = (gs.params->box_hsize - 1) / 2, box_vrad = (gs.params->box_vsize - 1) / 2;
     const int center = p.y * cols + p.x;
-    out[center] = pmCostMultiview_cu<float>(gs.imgs, hx_tile, tile_offset, p, planes[center], box_vrad,
+    out[center] = pmCostMultiview_cu<T>(gs.imgs, hx_tile, tile_offset, p, planes[center], box_vrad,
                                             box_hrad, *gs.params, *gs.cameras, planes, 0);
 }
 
@@ -273,13 +277,25 @@ extern "C" int hx_steps(const hx_params* prm, int rows, int cols, int n_images, 
     dim3 grid, block, grid16, block16;
     int smem_elems = 0;
     ref_setup_tiles(gs, grid, block, grid16, block16, smem_elems);
-    size_t smem = (size_t)smem_elems * sizeof(float);
+    const bool col = prm->color_processing != 0;
+    size_t smem = (size_t)smem_elems * (col ? sizeof(float4) : sizeof(float));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);  cudaEventCreate(&e1);
     for (int s = 0; s < n_steps; s++) {
         cudaDeviceSynchronize();
         cudaEventRecord(e0);
-        switch (steps[s]) {
+        if (col) switch (steps[s]) {
+        case HX_STEP_INIT:         gipuma_init_cu2<float4><<<grid16, block16>>>(gs); break;
+        case HX_STEP_BLACK_CLOSE:  gipuma_black_spatialPropClose_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_BLACK_FAR:    gipuma_black_spatialPropFar_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_BLACK_REFINE: gipuma_black_planeRefine_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_RED_CLOSE:    gipuma_red_spatialPropClose_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_RED_FAR:      gipuma_red_spatialPropFar_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_RED_REFINE:   gipuma_red_planeRefine_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_COMPUTE_DISP: gipuma_compute_disp<<<grid16, block16>>>(gs); break;
+        default: break;
+        }
+        else switch (steps[s]) {
         case HX_STEP_INIT:         gipuma_init_cu2<float><<<grid16, block16>>>(gs); break;
         case HX_STEP_BLACK_CLOSE:  gipuma_black_spatialPropClose_cu<float><<<grid, block, smem>>>(gs, 0); break;
         case HX_STEP_BLACK_FAR:    gipuma_black_spatialPropFar_cu<float><<<grid, block, smem>>>(gs, 0); break;
@@ -323,8 +339,10 @@ extern "C" int hx_cost_eval(const hx_params* prm, int rows, int cols, int n_imag
     checkCudaErrors(hx_malloc_zero((void**)&d_planes, n * sizeof(float4)));
     checkCudaErrors(hx_malloc_zero((void**)&d_out, n * sizeof(float)));
     cudaMemcpy(d_planes, planes, n * sizeof(float4), cudaMemcpyHostToDevice);
-    for (int color = 0; color < 2; color++)
-        hx_cost_eval_kernel<<<grid, block, smem_elems * sizeof(float)>>>(gs, d_planes, d_out, color);
+    for (int color = 0; color < 2; color++) {
+        if (prm->color_processing) hx_cost_eval_kernel<float4><<<grid, block, smem_elems * sizeof(float4)>>>(gs, d_planes, d_out, color);
+        else hx_cost_eval_kernel<float><<<grid, block, smem_elems * sizeof(float)>>>(gs, d_planes, d_out, color);
+    }
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) fprintf(stderr, "hx_cost_eval: %s\n", cudaGetErrorString(err));
     cudaMemcpy(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost);

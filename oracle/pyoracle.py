@@ -50,6 +50,7 @@ class Oracle:
                                               C.POINTER(C.c_uint32), fp]
 
     def _common(self):
+        self.lib.gpo_set_color(int(self.ref_img.ndim == 3))          # [H, W, 4] images: the float4 path
         return (self.W, self.H, self.V, C.byref(self.prm), C.byref(self.ref), self.views,
                 self.ref_img.ctypes.data_as(C.POINTER(C.c_float)), self.vptrs)
 

@@ -64,6 +64,72 @@ def test_full_run_bit_exact_vs_live_reference(cfg, rows, cols, views, iters, box
     assert bits_equal(ls.c, r_c) == 0
 
 
+COLOR_CASES = [
+    # rows, cols, views, iters, box, n_best, cost_comb, seed      (float4 tile of box > 21 exceeds the reference's 48 KB)
+    (96, 128, 5, 2, 11, 3, 1, 31337),
+    (64, 96, 3, 2, 19, 2, 1, 7),
+    (64, 96, 6, 2, 7, 3, 3, 11),                      # COMB_GOOD
+    (64, 96, 6, 1, 5, 8, 0, 12),                      # COMB_ALL
+    (64, 64, 4, 3, 21, 3, 1, 123),                    # border-heavy, largest float4 window the reference can launch
+    (64, 96, 33, 1, 5, 3, 1, 3),                      # > 32 views
+]
+
+
+@pytest.mark.parametrize("rows,cols,views,iters,box,nbest,comb,seed", COLOR_CASES)
+def test_color_processing_full_run_bit_exact_vs_live_reference(rows, cols, views, iters, box, nbest, comb, seed):
+    """-color_processing: float4 images, runcuda<float4> (gipuma.cu:1965-1966)."""
+    from gipuma_b200 import api, scene as S
+    sc = S.colorize(S.make_config(4 if views > 10 else 2, rows=rows, cols=cols, n_views=views, iterations=iters,
+                                  seed=2000 + seed))
+    sc.params.box_hsize = sc.params.box_vsize = box
+    sc.params.n_best = nbest
+    sc.params.cost_comb = comb
+    assert reference_tile_fully_loaded(rows, cols, box)
+    ref = _ref(sc.n_views)
+    r_n4, r_c, _, _ = ref.run(sc, seed=seed)
+    for opts in ({}, {"memo": 0, "prune": 0, "dedupe": 0}):
+        ls, _, _ = api.runcuda(sc, seed=seed, options=opts)
+        assert bits_equal(ls.norm4, r_n4) == 0
+        assert bits_equal(ls.c, r_c) == 0
+
+
+def test_color_every_kernel_of_one_iteration_vs_live_reference():
+    from gipuma_b200 import api, scene as S
+    from oracle import pyref
+    sc = S.colorize(S.make_config(2, rows=96, cols=128, n_views=6, iterations=1, seed=4243))
+    sc.params.box_hsize = sc.params.box_vsize = 13
+    ref = _ref(sc.n_views)
+    n4, c, _ = ref.steps(sc, [pyref.STEP_INIT], seed=99)
+    with api.Context(sc.cols, sc.rows, sc.n_views) as ctx:
+        ctx.load_scene(sc, seed=99)
+        ctx.init()
+        m4, mc = ctx.get_state()
+        assert bits_equal(m4, n4) == 0 and bits_equal(mc, c) == 0
+        ctx.set_option("cost_variant", 2)                 # the initialisation kernel's rounding, on its own planes
+        assert bits_equal(ctx.cost_eval(n4), c) == 0
+        for step, (colour, mask) in zip(range(1, 7), [(0, 1), (0, 2), (0, 4), (1, 1), (1, 2), (1, 4)]):
+            n4, c, _ = ref.steps(sc, [step], norm4=n4, cost=c, seed=99)
+            ctx.phase(colour, mask)
+            m4, mc = ctx.get_state()
+            assert bits_equal(m4, n4) == 0, "planes differ after reference kernel %d" % step
+            assert bits_equal(mc, c) == 0, "costs differ after reference kernel %d" % step
+        n4, c, _ = ref.steps(sc, [pyref.STEP_COMPUTE_DISP], norm4=n4, cost=c)
+        ctx.finalize()
+        m4, mc = ctx.get_state()
+        assert bits_equal(m4, n4) == 0
+
+
+def test_color_and_gray_images_cannot_be_mixed():
+    from gipuma_b200 import api, scene as S
+    sc = S.make_config(2, rows=64, cols=96, n_views=2, iterations=1, seed=1)
+    cs = S.colorize(sc)
+    with api.Context(sc.cols, sc.rows, sc.n_views) as ctx:
+        ctx.set_params(sc.params)
+        ctx.set_reference(np.ascontiguousarray(cs.images[0]), cs.cameras[0])
+        with pytest.raises(api.GipumaError):
+            ctx.set_view(0, np.ascontiguousarray(sc.images[1]), sc.cameras[1])
+
+
 def test_ragged_image_size_init_and_cost_bit_exact():
     """75 x 53 (no multiple of 32 or 16, narrower than two tiles).  The reference's sweep kernels read unloaded
     shared memory for such shapes, so only the stages that do not depend on its tile loader are compared:

@@ -72,6 +72,15 @@ def test_view_shard_equals_single_context(cfg, rows, cols, views, world, box, nb
         assert bits_equal(c, single.c) == 0
 
 
+def test_view_shard_color_images():
+    from gipuma_b200 import api, scene as S
+    sc = S.colorize(S.make_config(2, rows=64, cols=96, n_views=5, iterations=2, seed=556))
+    sc.params.box_hsize = sc.params.box_vsize = 9
+    single, _, _ = api.runcuda(sc, seed=0xC0FFEE)
+    for n4, c in _sharded_run(sc, 2):
+        assert bits_equal(n4, single.norm4) == 0 and bits_equal(c, single.c) == 0
+
+
 def test_view_shard_refuses_other_combinations():
     import torch
     from gipuma_b200 import api, scene as S

@@ -115,3 +115,21 @@ def test_oracle_black_sweep_agrees_with_reference_decisions(golden):
     sel = black & same_as_some_initial
     agree = np.all(pl[ys, xs][sel] == ref4[ys, xs][sel], axis=-1)
     assert sel.sum() > 50 and agree.mean() > 0.97
+
+
+def test_color_restatement_reduces_to_gray_for_equal_channels(small_scene):
+    """T = float4 (gipuma.cu:173-178): with the gray image in all three channels every l1_norm(float4) is the gray
+    |difference| up to the 0.3333333f factor, so costs agree to ~1e-6 relative."""
+    import dataclasses
+    from oracle.pyoracle import Oracle
+    sc = small_scene
+    g4 = np.stack([sc.images] * 3 + [np.zeros_like(sc.images)], axis=-1)
+    cs = dataclasses.replace(sc, images=np.ascontiguousarray(g4),
+                             params=dataclasses.replace(sc.params, color_processing=True))
+    planes = np.zeros((sc.rows, sc.cols, 4), np.float32)
+    planes[..., 2] = -1.0
+    planes[..., 3] = 0.5 * (sc.params.depthMin + sc.params.depthMax)        # fronto-parallel, mid range
+    a = Oracle(sc).cost_eval(planes, y0=4, y1=8)[4:8]
+    b = Oracle(cs).cost_eval(planes, y0=4, y1=8)[4:8]
+    assert np.all(np.abs(a - b) <= 2e-6 * np.maximum(1.0, a))
+    assert a.std() > 0

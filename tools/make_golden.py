@@ -23,16 +23,22 @@ CASES = {
     "gB_box11_v5": (2, 64, 96, 5, 2, 11, 3),
     "gC_box11_v34": (4, 64, 96, 34, 1, 11, 3),
     "gD_box25_v3": (3, 64, 96, 3, 1, 25, 2),
+    "gE_color_box11_v4": (2, 64, 96, 4, 2, 11, 3),      # -color_processing: float4 images (S.colorize)
 }
 
 
 def main():
     out_dir = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden"
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[2:]
     for name, (cfg, rows, cols, views, iters, box, nbest) in CASES.items():
+        if only and name not in only:
+            continue
         sc = S.make_config(cfg, rows=rows, cols=cols, n_views=views, iterations=iters)
         sc.params.box_hsize = sc.params.box_vsize = box
         sc.params.n_best = nbest
+        if "color" in name:
+            sc = S.colorize(sc)
         h = pyref.Harness("ref64" if sc.n_views > 32 else "ref")
         seed = 0xC0FFEE
         i_n4, i_c, _ = h.steps(sc, [0], seed=seed)

@@ -11,10 +11,13 @@ ap.add_argument("--iters", type=int, default=None)
 ap.add_argument("--rows", type=int, default=None)
 ap.add_argument("--cols", type=int, default=None)
 ap.add_argument("--views", type=int, default=None)
+ap.add_argument("--color", action="store_true", help="float4 images (-color_processing)")
 ap.add_argument("--repeat", type=int, default=2)
 ap.add_argument("--opt", nargs="*", default=[])
 args = ap.parse_args()
 sc = S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters)
+if args.color:
+    sc = S.colorize(sc)
 opts = {k: int(v) for k, v in (o.split("=") for o in args.opt)}
 out = {"config": sc.name, "rows": sc.rows, "cols": sc.cols, "views": sc.n_views, "iters": sc.params.iterations, "opts": opts, "runs": []}
 with api.Context(sc.cols, sc.rows, sc.n_views) as ctx:

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--cols", type=int, default=None)
     ap.add_argument("--views", type=int, default=None)
+    ap.add_argument("--color", action="store_true", help="float4 images (-color_processing)")
     ap.add_argument("--save", type=str, default=None)
     ap.add_argument("--steps", action="store_true", help="also time each kernel of one iteration (hx_steps)")
     ap.add_argument("--repeat", type=int, default=1)
@@ -31,6 +32,8 @@ def main():
 
     t0 = time.time()
     sc = S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters)
+    if args.color:
+        sc = S.colorize(sc)
     t_scene = time.time() - t0
     h = pyref.Harness("ref64" if sc.n_views > 32 else "ref")
     out = {"config": sc.name, "rows": sc.rows, "cols": sc.cols, "views": sc.n_views, "iters": sc.params.iterations,
