@@ -14,7 +14,9 @@
 #include "../../include/gipuma_b200.h"
 #include "gpm_kernels.cuh"
 
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,9 +50,10 @@ struct gpm_ctx {
     float* dispbuf = nullptr;        // view-shard mode: disp_now carried between the stages of one colour
     float4* candbuf = nullptr;       // view-shard mode: refinement candidate of the current step
     float* canddepth = nullptr;
-    float4* seen = nullptr;          // [H*W*8] last plane offered to each pixel from each of the 8 propagation directions
+    float4* seen = nullptr;          // [H*W*ncand] last plane offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
+    int seen_slots = 8;
     float4* refseen = nullptr;       // [H*W]   plane from which the last all-rejected refinement started
-    unsigned short* memo_mask = nullptr;   // [H*W] validity bits of seen (0-7) and refseen (8)
+    unsigned* memo_mask = nullptr;   // [H*W] validity bits of seen (0-19) and refseen (GPM_MEMO_REFINE)
     unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
     int refpitch = 0;
@@ -78,6 +81,8 @@ struct gpm_ctx {
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
     int opt_cost_variant = -1, opt_packed = 0, opt_memo = 1;
+    int opt_neighbours = 8;                      // 20: the reference's fused kernel (built when SMALLKERNEL is not defined)
+    int opt_site[21];                            // diagnostics: override the fused kernel's call-site variants (-1 = table)
     int smem_optin = 0, num_sms = 148;
 };
 
@@ -127,11 +132,20 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     P.dedupe_self = c->opt_dedupe ? 1 : 0;
     // rounding variant of k_cost_eval: at initialisation the reference's binary is y-first for float, x-first for float4;
     // gpm_cost_eval defaults to the variant of the propagation kernels (x-first for float, y-first for float4)
-    // (option cost_variant 2 = the initialisation form).  For float4 the initialisation kernel additionally folds the
-    // other gradient term into the FMA (grad_variant).
+    // For float4 the initialisation kernel additionally folds the other gradient term into the FMA (grad_variant).
+    // Option cost_variant: bit 0 = x-term first, bit 1 = gradient folding (float4 only).
     const int cv = eval_call ? c->opt_cost_variant : -1;          // the option only steers gpm_cost_eval
-    P.cost_variant = (init_phase || cv == 2) ? (c->color == 1 ? 1 : 0) : (cv >= 0 ? cv : (c->color == 1 ? 0 : 1));
-    P.grad_variant = (c->color == 1 && (init_phase || cv == 2)) ? 1 : 0;
+    P.cost_rt = 0;
+    if (init_phase) { P.cost_variant = c->color == 1 ? 1 : 0;  P.grad_variant = c->color == 1 ? 1 : 0; }
+    else if (cv >= 0) { P.cost_variant = cv & 1;  P.grad_variant = (c->color == 1) ? ((cv >> 1) & 1) : 0;  P.cost_rt = c->color == 1 ? cv : (cv & ~2); }
+    else { P.cost_variant = c->color == 1 ? 0 : 1;  P.grad_variant = 0; }
+    P.ncand = c->opt_neighbours == 20 ? 20 : 8;
+    // call-site variants of the fused kernels, read off the reference build (tools/fused_probe.py)
+    {
+        static const unsigned char kSitesFloat[21] = GPM_FUSED_SITES_FLOAT, kSitesFloat4[21] = GPM_FUSED_SITES_FLOAT4;
+        for (int k = 0; k < 21; k++)
+            P.site[k] = c->opt_site[k] >= 0 ? (unsigned char)c->opt_site[k] : (c->color == 1 ? kSitesFloat4[k] : kSitesFloat[k]);
+    }
     P.color = c->color == 1 ? 1 : 0;
     P.memo = c->opt_memo;
     P.packed = c->opt_packed;
@@ -178,7 +192,9 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
     int split = 1;
     while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
     grid.z = split;
-    (P.color ? k_sweep<false, true> : (P.packed ? k_sweep<true, false> : k_sweep<false, false>))<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
+    auto kern = P.ncand == 20 ? (P.color ? k_sweep<false, true, true> : k_sweep<false, false, true>)
+                              : (P.color ? k_sweep<false, true, false> : (P.packed ? k_sweep<true, false, false> : k_sweep<false, false, false>));
+    kern<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
                                                       c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -232,6 +248,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     if (device < 0 || device >= ndev) return fail(GPM_E_ARG, "gpm_create: no such device");
     DeviceGuard g(device);
     gpm_ctx* c = new gpm_ctx;
+    for (int& v : c->opt_site) v = -1;
     c->device = device;  c->W = width;  c->H = height;  c->maxV = max_views;
     c->have_view.assign(max_views, 0);
     c->view_8bit.assign(max_views, 0);
@@ -248,7 +265,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->prov, n));
     ok(cudaMalloc(&c->seen, n * 8 * sizeof(float4)));
     ok(cudaMalloc(&c->refseen, n * sizeof(float4)));
-    ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned short)));
+    ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned)));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
     ok(cudaMalloc(&c->d_flag, sizeof(int)));
     ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
@@ -257,8 +274,8 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     if (err == cudaSuccess) {
         ok(cudaMemsetAsync(c->planes, 0, n * sizeof(float4), c->stream));      // LineState::resize zeroes (linestate.h:19-24)
         ok(cudaMemsetAsync(c->cost, 0, n * sizeof(float), c->stream));
-        ok(cudaMemsetAsync(c->prov, 2, n, c->stream));
-        ok(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned short), c->stream));
+        ok(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, n, c->stream));
+        ok(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned), c->stream));
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
@@ -273,9 +290,11 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaCreateTextureObject(&c->srcTex, &res, &td, NULL));
         ok(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         ok(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-        ok(cudaFuncSetAttribute(k_sweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_sweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_sweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_sweep<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
@@ -326,7 +345,7 @@ extern "C" int gpm_set_params(gpm_ctx* c, const gpm_params* p)
     c->have_params = true;
     {
         DeviceGuard g(c->device);
-        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));   // memo depends on the parameters
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));   // memo depends on the parameters
     }
     return GPM_OK;
 }
@@ -344,7 +363,7 @@ extern "C" int gpm_set_rng(gpm_ctx* c, unsigned long long seed, int mode)
     DeviceGuard g(c->device);
     c->seed = seed;
     c->rng_mode = mode;
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     if (mode == GPM_RNG_STATEFUL && !c->rng) {
         CU(cudaMalloc(&c->rng, (size_t)c->W * c->H * 6 * sizeof(unsigned)));
         CU(cudaMemsetAsync(c->rng, 0, (size_t)c->W * c->H * 6 * sizeof(unsigned), c->stream));
@@ -366,8 +385,8 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
     return GPM_OK;
 }
@@ -422,8 +441,8 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     memcpy(vc.t, cam->t, sizeof(vc.t));
     c->cams_dirty = true;
     c->have_view[v] = 1;
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));        // staging buffers are reused; the caller may reuse its buffer
     return GPM_OK;
 }
@@ -475,8 +494,8 @@ extern "C" int gpm_set_reference_color(gpm_ctx* c, const float* rgba, size_t pit
     k_pad_reference4<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->refpad4, c->refpitch);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
@@ -506,8 +525,8 @@ extern "C" int gpm_set_view_color(gpm_ctx* c, int v, const float* rgba, size_t p
     c->cams_dirty = true;
     c->have_view[v] = 1;
     c->view_8bit[v] = 0;
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
@@ -522,8 +541,8 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
     // provenance of the supplied costs is unknown (2) unless the caller vouches that they came from an
     // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
-    CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? (c->color == 1 ? 1 : 0) : 2, n, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? (c->color == 1 ? 3 : 0) : GPM_PROV_UNKNOWN, n, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
@@ -556,8 +575,8 @@ static int do_init(gpm_ctx* c)
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(c->prov, c->color == 1 ? 1 : 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));
+    CU(cudaMemsetAsync(c->prov, c->color == 1 ? 3 : 0, (size_t)c->W * c->H, c->stream));   // costs now come from the init-variant evaluation (float4: x-first + gradient folding 1)
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     return GPM_OK;
 }
 
@@ -586,8 +605,8 @@ static int do_finalize(gpm_ctx* c)
     k_finalize<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(c->prov, 2, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned short), c->stream));   // planes are world-frame outputs now
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));   // planes are world-frame outputs now
     return GPM_OK;
 }
 
@@ -713,6 +732,7 @@ extern "C" long long gpm_shard_stage_floats(gpm_ctx* c, int stage)
 static int shard_common(gpm_ctx* c, int stage, KParams& P)
 {
     if (c->prm.cost_comb != GPM_COMB_BEST_N) return fail(GPM_E_ARG, "view sharding supports cost_comb = best_n only");
+    if (c->opt_neighbours != 8) return fail(GPM_E_ARG, "view sharding supports the 8-neighbour sweep only (option neighbours = 8)");
     if (c->prm.n_best < 1 || c->prm.n_best > 32) return fail(GPM_E_ARG, "view sharding needs 1 <= n_best <= 32");
     if (stage < 0 || stage >= 2 + shard_refine_steps(c->prm)) return fail(GPM_E_ARG, "no such stage");
     int rc = build_kparams(c, stage == 0, P);
@@ -804,7 +824,26 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "trust_state") c->opt_trust_state = value != 0;
     else if (n == "nwarps") c->opt_nwarps = value;
     else if (n == "stats") c->opt_stats = value != 0;
-    else if (n == "cost_variant") c->opt_cost_variant = value < 0 ? -1 : (value > 2 ? 1 : value);
+    else if (n == "cost_variant") c->opt_cost_variant = value < 0 ? -1 : (value & 15);
+    else if (n.rfind("site", 0) == 0 && n.size() > 4 && n.size() <= 6 && std::isdigit((unsigned char)n[4])) {
+        const int k = std::atoi(n.c_str() + 4);             // "site<k>": variant of call site k of the fused kernel (diagnostics)
+        if (k < 0 || k > 20) return fail(GPM_E_ARG, "site index out of range");
+        c->opt_site[k] = value < 0 ? -1 : (value & 15);
+    }
+    else if (n == "neighbours") {
+        if (value != 8 && value != 20) return fail(GPM_E_ARG, "neighbours must be 8 (close + far kernels) or 20 (fused kernel)");
+        DeviceGuard g(c->device);
+        if (value == 20) c->opt_packed = 0;
+        const int slots = value == 20 ? 20 : 8;
+        if (slots != c->seen_slots) {
+            CU(cudaStreamSynchronize(c->stream));
+            cudaFree(c->seen);  c->seen = nullptr;
+            CU(cudaMalloc(&c->seen, (size_t)c->W * c->H * slots * sizeof(float4)));
+            c->seen_slots = slots;
+        }
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
+        c->opt_neighbours = value;
+    }
     else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");

@@ -113,8 +113,9 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
         setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
         const float inf = __int_as_float(0x7f800000);
-        const float c = P.cost_variant ? eval_plane<true, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
-                                       : eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
+        const float c = (P.cost_rt & 12) ? eval_plane<2, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st, nullptr, nullptr, (unsigned)P.cost_rt)
+                        : P.cost_variant ? eval_plane<1, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st)
+                                         : eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st);
         if (lane == 0) cost[(size_t)py * P.W + px] = c;
     }
     flush_stats(stats, st, lane);
@@ -123,12 +124,22 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
 // ---- one checkerboard colour: close + far propagation + refinement, fused --------------------
 // gipuma_{black,red}_spatialPropClose_cu / spatialPropFar_cu / planeRefine_cu, gipuma.cu:1353-1823.
 // colour 0 = black, 1 = red; phase_mask bit0 close, bit1 far, bit2 refine.
-template <bool PACKED, bool COLOR>
+// Candidate table of the fused 20-neighbour kernel gipuma_checkerboard_cu (gipuma.cu:1236-1330): offset of candidate k
+// and the reference's own border guards, written as margins  x >= gx0, x <= W-1-gx1, y >= gy0, y <= H-1-gy1
+// (they are not the tightest ones: e.g. `left - cols*2` is guarded by p.y > 2, gipuma.cu:1313-1317).
+__device__ const signed char kFusedDx[20]  = { 0,  0,  0, 0, 0, 0, -1, -3, -5, 1, 3, 5,  2, 2, -2, -2, -1,  1, -1, 1};
+__device__ const signed char kFusedDy[20]  = {-1, -3, -5, 1, 3, 5,  0,  0,  0, 0, 0, 0, -1, 1, -1,  1, -2, -2,  2, 2};
+__device__ const signed char kFusedGx0[20] = { 0,  0,  0, 0, 0, 0,  1,  3,  5, 0, 0, 0,  0, 0,  2,  2,  1,  0,  1, 0};
+__device__ const signed char kFusedGx1[20] = { 0,  0,  0, 0, 0, 0,  0,  0,  0, 1, 3, 5,  2, 2,  0,  0,  0,  1,  0, 1};
+__device__ const signed char kFusedGy0[20] = { 1,  3,  5, 0, 0, 0,  0,  0,  0, 0, 0, 0,  1, 0,  1,  0,  3,  3,  0, 0};
+__device__ const signed char kFusedGy1[20] = { 0,  0,  0, 1, 3, 5,  0,  0,  0, 0, 0, 0,  0, 1,  0,  1,  0,  0,  2, 2};
+
+template <bool PACKED, bool COLOR, bool FUSED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
         unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, float4* __restrict__ seen,
-        float4* __restrict__ refseen, unsigned short* __restrict__ memo_mask, int colour, int phase_mask,
+        float4* __restrict__ refseen, unsigned* __restrict__ memo_mask, int colour, int phase_mask,
         unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(16) float smem[];
@@ -166,10 +177,19 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             // which rounding variant of the cost function produced cost_now: 0 = y-first (XFIRST false), 1 = x-first, 2 = unknown
             int prov_now = prov[center];
 
-            // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462)
+            // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462);
+            // fused kernel: the 20 candidates of gipuma.cu:1236-1330 in source order
+            constexpr int NC = FUSED ? 20 : 8;
+            constexpr unsigned NCMASK = (1u << NC) - 1u;
             float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
             bool mine_ok = false;
-            if (lane < 8) {
+            if (FUSED) {
+                if (lane < NC) {
+                    mine_ok = (phase_mask & 1) && px >= kFusedGx0[lane] && px <= W - 1 - kFusedGx1[lane] &&
+                              py >= kFusedGy0[lane] && py <= H - 1 - kFusedGy1[lane];
+                    if (mine_ok) mine = planes[(size_t)(py + kFusedDy[lane]) * W + (px + kFusedDx[lane])];
+                }
+            } else if (lane < 8) {
                 const int dist = lane < 4 ? 1 : 5;
                 const int dir = lane & 3;
                 const bool phase_on = (phase_mask >> (lane >> 2)) & 1;
@@ -186,21 +206,27 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             // function, so a neighbour plane this pixel has already been offered — accepted or not — can never be
             // accepted later: seen[p][k] holds the last plane offered from direction k; an unchanged neighbour is skipped
             // without evaluation, in every later iteration.  Exact, not a heuristic.
-            unsigned short mmask = P.memo ? memo_mask[center] : (unsigned short)0;
-            const bool old_ok = P.memo && lane < 8 && ((mmask >> lane) & 1);
+            // the cost function of the fused kernel differs between its inlined call sites (P.site): the duplicate / memo
+            // shortcuts below only pair candidates of sites with the same rounding variant
+            const unsigned my_site = FUSED ? (unsigned)P.site[lane < NC ? lane : 0] : (COLOR ? 0u : 1u);
+            unsigned mmask = P.memo ? memo_mask[center] : 0u;
+            const bool old_ok = P.memo && lane < NC && ((mmask >> lane) & 1);
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (old_ok) old = seen[center * 8 + lane];
+            if (old_ok) old = seen[center * NC + lane];
             const bool memo_hit = old_ok && mine_ok &&
                                   __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
                                   __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
-            for (int k = 0; k < 8; k++) {
+            for (int k = 0; k < NC; k++) {
                 if (!((cand_mask >> k) & 1)) continue;
+                // rounding variant of this call site: x-first for float images, y-first for float4; the fused
+                // kernel's inlined sites are looked up (bit 0 = x-first, bit 1 = gradient folding)
+                const unsigned site = FUSED ? (unsigned)P.site[k] : (COLOR ? 0u : 1u);
                 float4 nb;
                 nb.x = __shfl_sync(GPM_FULL, mine.x, k);  nb.y = __shfl_sync(GPM_FULL, mine.y, k);
                 nb.z = __shfl_sync(GPM_FULL, mine.z, k);  nb.w = __shfl_sync(GPM_FULL, mine.w, k);
                 // already offered to this pixel before, from ANY direction (the 8 memo entries double as a history)?
-                const bool known = old_ok && __float_as_uint(nb.x) == __float_as_uint(old.x) && __float_as_uint(nb.y) == __float_as_uint(old.y) &&
+                const bool known = old_ok && my_site == site && __float_as_uint(nb.x) == __float_as_uint(old.x) && __float_as_uint(nb.y) == __float_as_uint(old.y) &&
                                    __float_as_uint(nb.z) == __float_as_uint(old.z) && __float_as_uint(nb.w) == __float_as_uint(old.w);
                 if (__any_sync(GPM_FULL, known)) { st.skip++; continue; }
                 // spatialPropagation_cu, gipuma.cu:832-874
@@ -208,34 +234,34 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                 const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
                 // exact duplicates: cost(p, plane) is a pure function, so a plane equal to the current one or to an
                 // earlier candidate of this pixel cannot be accepted (`cost_before < *cost_now` is false)
-                const bool same_now = P.dedupe_self && prov_now == (COLOR ? 0 : 1) &&
+                const bool same_now = P.dedupe_self && prov_now == (int)site &&
                                       __float_as_uint(nb.x) == __float_as_uint(norm_now.x) && __float_as_uint(nb.y) == __float_as_uint(norm_now.y) &&
                                       __float_as_uint(nb.z) == __float_as_uint(norm_now.z) && __float_as_uint(nb.w) == __float_as_uint(norm_now.w);
-                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
+                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && my_site == site &&
                                        __float_as_uint(nb.x) == __float_as_uint(mine.x) && __float_as_uint(nb.y) == __float_as_uint(mine.y) &&
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
                 if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
-                // rounding variant of the propagation kernels: x-first for float images, y-first for float4
-                const float c = eval_plane<!COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
+                const float c = FUSED ? eval_plane<2, PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st, nullptr, nullptr, site)
+                                      : eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
                     disp_now = disp_before;
                     norm_now = nb;
                     cost_now = c;
-                    prov_now = COLOR ? 0 : 1;
+                    prov_now = (int)site;
                 }
             }
 
             if (P.memo && mine_ok && !memo_hit) {            // every candidate offered above is now known to this pixel
-                seen[center * 8 + lane] = mine;
+                seen[center * NC + lane] = mine;
             }
-            unsigned short new_mask = (unsigned short)(mmask | (cand_mask & 0xffu));
+            unsigned new_mask = mmask | (cand_mask & NCMASK);
             // The refinement candidates are a pure function of (pixel, plane at refinement start) in GPM_RNG_REFERENCE
             // mode (zero-state stream; disp_now == plane_depth(norm_now) here), so a refinement that rejected all its steps
             // from exactly this plane before would reject them again.
             bool refine = (phase_mask & 4) != 0;
-            if (refine && P.memo && P.rng_mode == 0 && ((mmask >> 8) & 1)) {
+            if (refine && P.memo && P.rng_mode == 0 && (mmask & GPM_MEMO_REFINE)) {
                 const float4 old = refseen[center];
                 if (__float_as_uint(old.x) == __float_as_uint(norm_now.x) && __float_as_uint(old.y) == __float_as_uint(norm_now.y) &&
                     __float_as_uint(old.z) == __float_as_uint(norm_now.z) && __float_as_uint(old.w) == __float_as_uint(norm_now.w)) {
@@ -274,9 +300,11 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
                     if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
                     cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);   // :969
-                    const float c = eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
+                    const unsigned rsite = FUSED ? (unsigned)P.site[20] : 0u;
+                    const float c = FUSED ? eval_plane<2, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st, nullptr, nullptr, rsite)
+                                          : eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, cost_now, lane, st);
                     if (c < cost_now) {                                                          // :986-990 (no depth-range test)
-                        prov_now = 0;
+                        prov_now = (int)rsite;
                         any_accept = true;
                         cost_now = c;
                         disp_now = depth_new;
@@ -289,8 +317,8 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
                     o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
                 }
                 if (P.memo && P.rng_mode == 0) {
-                    if (!any_accept) { if (lane == 0) refseen[center] = norm_start;  new_mask |= 0x100; }
-                    else new_mask &= (unsigned short)~0x100;
+                    if (!any_accept) { if (lane == 0) refseen[center] = norm_start;  new_mask |= GPM_MEMO_REFINE; }
+                    else new_mask &= ~GPM_MEMO_REFINE;
                 }
             }
             if (P.memo && lane == 0 && new_mask != mmask) memo_mask[center] = new_mask;
@@ -324,7 +352,7 @@ __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
              cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
              const unsigned char* __restrict__ prov, float* __restrict__ dispbuf, float4* __restrict__ candbuf,
-             float* __restrict__ canddepth, float4* __restrict__ seen, unsigned short* __restrict__ memo_mask,
+             float* __restrict__ canddepth, float4* __restrict__ seen, unsigned* __restrict__ memo_mask,
              int colour, int stage, float* __restrict__ xchg)
 {
     extern __shared__ __align__(16) float smem[];
@@ -356,7 +384,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
         const float4 norm_now = planes[center];
         float c0, c1;
         if (stage == 0) {
-            eval_plane<COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);   // init variant
+            eval_plane<(COLOR ? 1 : 0), PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);   // init variant
             local_topn(P, c0, c1, lane, out);
         } else if (stage == 1) {
             const int prov_now = prov[center];
@@ -375,7 +403,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                 if (mine_ok) mine = planes[(size_t)qy * W + qx];
             }
             // direction memo of rejected work, as in k_sweep (identical on every rank: it only depends on the shared state)
-            const unsigned short mmask = P.memo ? memo_mask[center] : (unsigned short)0;
+            const unsigned mmask = P.memo ? memo_mask[center] : 0u;
             bool memo_hit = false;
             if (P.memo && mine_ok && ((mmask >> lane) & 1)) {
                 const float4 old = seen[center * 8 + lane];
@@ -385,7 +413,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
             const unsigned memo_bits = __ballot_sync(GPM_FULL, memo_hit);
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
             if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
-            if (P.memo && lane == 0 && (unsigned short)(mmask | (cand_mask & 0xffu)) != mmask) memo_mask[center] = (unsigned short)(mmask | (cand_mask & 0xffu));
+            if (P.memo && lane == 0 && (mmask | (cand_mask & 0xffu)) != mmask) memo_mask[center] = mmask | (cand_mask & 0xffu);
             for (int k = 0; k < 8; k++) {
                 float4 nbp;
                 nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
@@ -396,14 +424,13 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
                     const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
                     // self-dedupe is only neutral against the cost at kernel entry if no earlier slot is accepted; the
                     // accept kernel cannot know, so only the candidate-vs-candidate rule is used here
-                    const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&
-                                           __float_as_uint(nbp.x) == __float_as_uint(mine.x) && __float_as_uint(nbp.y) == __float_as_uint(mine.y) &&
+                    const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&                                            __float_as_uint(nbp.x) == __float_as_uint(mine.x) && __float_as_uint(nbp.y) == __float_as_uint(mine.y) &&
                                            __float_as_uint(nbp.z) == __float_as_uint(mine.z) && __float_as_uint(nbp.w) == __float_as_uint(mine.w);
                     skip = !in_range || __any_sync(GPM_FULL, same_mine);
                     (void)prov_now;
                 }
                 if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-                eval_plane<!COLOR, PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+                eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
                 local_topn(P, c0, c1, lane, out + k * nb);
             }
         } else {
@@ -433,7 +460,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
             if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
             cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
             if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
-            eval_plane<false, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         }
     }
@@ -481,7 +508,7 @@ __global__ void k_shard_accept(const __grid_constant__ KParams P, float4* __rest
         const float* g = gathered + (((stage == 0 ? (size_t)col * H * Wh : 0) + (size_t)py * Wh + hx) * slots) * nb;
         if (stage == 0) {
             cost[center] = shard_merge(g, per_rank, world, nb);
-            prov[center] = P.color ? 1 : 0;          // initialisation variant
+            prov[center] = P.color ? 3 : 0;          // initialisation variant
         } else if (stage == 1) {
             float4 norm_now = planes[center];
             float cost_now = cost[center];

@@ -105,6 +105,17 @@ int runcuda(GlobalState& gs)
                    : (unsigned long long)std::chrono::high_resolution_clock::now().time_since_epoch().count();
     }
     GPM_CHECK(gpm_set_rng(ctx, seed, GPM_RNG_REFERENCE));
+    // The reference picks its sweep at compile time: `#define SMALLKERNEL` (gipuma.cu:33, the shipped setting) runs the six
+    // 4-neighbour kernels per iteration, without it the fused 20-neighbour kernels (gipuma.cu:1913-1940).  Here: build the
+    // adapter with -DGPM_ADAPTER_NEIGHBOURS=20 or set GIPUMA_B200_NEIGHBOURS=20.
+#ifndef GPM_ADAPTER_NEIGHBOURS
+#define GPM_ADAPTER_NEIGHBOURS 8
+#endif
+    {
+        const char* env = getenv("GIPUMA_B200_NEIGHBOURS");
+        const int nb = env ? atoi(env) : GPM_ADAPTER_NEIGHBOURS;
+        if (nb != 8) GPM_CHECK(gpm_set_option(ctx, "neighbours", nb));
+    }
 
     size_t avail = 0, total = 0;
     cudaMemGetInfo(&avail, &total);

@@ -147,8 +147,11 @@ int gpm_reset_stats(gpm_ctx* ctx);
  * "trust_state" (0): treat a state loaded with gpm_set_state as cost-consistent; "nwarps" (0 = auto): warps per block;
  * "stats" (1): maintain the gpm_get_stats counters; "memo" (1): skip candidates / refinements this pixel is already
  * known to reject (exact); "cost_variant" (-1 = auto): which of the reference binary's rounding variants gpm_cost_eval
- * reproduces: 1 = x-term first (float: propagation kernels), 0 = y-term first (float: init / refinement; float4:
- * all six sweep kernels), 2 = the initialisation kernel's form; auto = the propagation kernels' form.
+ * reproduces: bit 0 = x-term first (float: 1 in the propagation kernels, 0 at init / refinement; float4: 0 in
+ * all six sweep kernels), bit 1 = float4 gradient folding (float4 initialisation = 3); auto = the propagation kernels' form;
+ * "neighbours" (8): 20 selects the reference's fused sweep — the kernels it launches when built without SMALLKERNEL
+ * (gipuma.cu:1122-1351, 1913-1940): 12 axial + 8 knight-move neighbours, then refinement, one launch per colour; bit-exact
+ * like the default (view sharding stays 8-neighbour only).
  * EXPERIMENTAL, not covered by the bit-exactness statement: "packed" (0 = off, 1 = auto, 2 = on) samples the source-view
  * gradients with one RG32F fetch instead of four R32F fetches for 8-bit images; measured 1 differing pixel in 1.92 M at cfg 2. */
 int gpm_set_option(gpm_ctx* ctx, const char* name, int value);

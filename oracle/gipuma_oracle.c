@@ -320,7 +320,8 @@ static void propagate(const gpo_scene* s, int px, int py, const float* nb, float
 }
 
 /* One phase set of one checkerboard colour, in place: colour 0 = black, 1 = red; phase_mask bit0 close
- * (gipuma.cu:1471-1588), bit1 far (:1353-1468), bit2 refine (:1590-1711, planeRefinement_cu :928-994 with an
+ * (gipuma.cu:1471-1588), bit1 far (:1353-1468), bit3 the 20 candidates of the fused kernel (:1122-1351, built when
+ * SMALLKERNEL is not defined), bit2 refine (:1590-1711, planeRefinement_cu :928-994 with an
  * all-zero XORWOW state per pixel — pin P2).  Pixel (x, y) is black iff (x + y) is even (:1730-1734).
  * A colour only reads the other colour's planes, so the pixel order inside a colour is irrelevant.
  * Restricted to rows [y0, y1) for bounded CPU timing. */
@@ -346,6 +347,20 @@ int gpo_phase(int W, int H, int V, const gpm_params* prm, const gpm_camera* ref,
                 if (py < H - d) propagate(&s, px, py, planes + 4 * (center + (size_t)d * W), &cost_now, norm_now, &disp_now, rad);
                 if (px > d - 1) propagate(&s, px, py, planes + 4 * (center - d), &cost_now, norm_now, &disp_now, rad);
                 if (px < W - d) propagate(&s, px, py, planes + 4 * (center + d), &cost_now, norm_now, &disp_now, rad);
+            }
+            if (phase_mask & 8) {
+                /* the fused kernel's 20 candidates in source order with the reference's own guards,
+                 * gipuma_checkerboard_cu, gipuma.cu:1236-1330 (EXTRAPOINT, EXTRAPOINTFAR, EXTRAPOINT2 all defined, :36-38) */
+                static const int dx[20] = {0, 0, 0, 0, 0, 0, -1, -3, -5, 1, 3, 5, 2, 2, -2, -2, -1, 1, -1, 1};
+                static const int dy[20] = {-1, -3, -5, 1, 3, 5, 0, 0, 0, 0, 0, 0, -1, 1, -1, 1, -2, -2, 2, 2};
+                const int guard[20] = {
+                    py > 0, py > 2, py > 4, py < H - 1, py < H - 3, py < H - 5,                 /* up, upup, up 5; down ... :1236-1264 */
+                    px > 0, px > 2, px > 4, px < W - 1, px < W - 3, px < W - 5,                 /* left ...; right ...      :1266-1292 */
+                    py > 0 && px < W - 2, py < H - 1 && px < W - 2, py > 0 && px > 1, py < H - 1 && px > 1,      /* :1295-1311 */
+                    px > 0 && py > 2, px < W - 1 && py > 2, px > 0 && py < H - 2, px < W - 1 && py < H - 2 };   /* :1312-1329 */
+                for (int k = 0; k < 20; k++)
+                    if (guard[k])
+                        propagate(&s, px, py, planes + 4 * ((size_t)(py + dy[k]) * W + (px + dx[k])), &cost_now, norm_now, &disp_now, rad);
             }
             if (phase_mask & 4) {
                 gpo_xorwow r;

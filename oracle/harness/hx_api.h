@@ -36,7 +36,10 @@ typedef struct hx_camera {               /* the Camera_cu fields main.cpp/camera
 } hx_camera;
 
 enum { HX_STEP_INIT = 0, HX_STEP_BLACK_CLOSE = 1, HX_STEP_BLACK_FAR = 2, HX_STEP_BLACK_REFINE = 3,
-       HX_STEP_RED_CLOSE = 4, HX_STEP_RED_FAR = 5, HX_STEP_RED_REFINE = 6, HX_STEP_COMPUTE_DISP = 7 };
+       HX_STEP_RED_CLOSE = 4, HX_STEP_RED_FAR = 5, HX_STEP_RED_REFINE = 6, HX_STEP_COMPUTE_DISP = 7,
+       /* the fused 20-neighbour kernels the reference launches when SMALLKERNEL is not defined (gipuma.cu:1714-1725,
+        * 1770-1781, 1937-1939): 12 axial + 8 knight-move neighbours, then plane refinement, one launch per colour */
+       HX_STEP_BLACK_FUSED = 8, HX_STEP_RED_FUSED = 9 };
 
 /* Full run through runcuda().  images: n_images x rows x cols float (index 0 = reference).
  * subset: indices into images/cams of the selected source views (viewSelectionSubset).

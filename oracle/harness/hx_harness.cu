@@ -293,6 +293,8 @@ extern "C" int hx_steps(const hx_params* prm, int rows, int cols, int n_images, 
         case HX_STEP_RED_FAR:      gipuma_red_spatialPropFar_cu<float4><<<grid, block, smem>>>(gs, 0); break;
         case HX_STEP_RED_REFINE:   gipuma_red_planeRefine_cu<float4><<<grid, block, smem>>>(gs, 0); break;
         case HX_STEP_COMPUTE_DISP: gipuma_compute_disp<<<grid16, block16>>>(gs); break;
+        case HX_STEP_BLACK_FUSED:  gipuma_black_cu<float4><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_RED_FUSED:    gipuma_red_cu<float4><<<grid, block, smem>>>(gs, 0); break;
         default: break;
         }
         else switch (steps[s]) {
@@ -304,6 +306,8 @@ extern "C" int hx_steps(const hx_params* prm, int rows, int cols, int n_images, 
         case HX_STEP_RED_FAR:      gipuma_red_spatialPropFar_cu<float><<<grid, block, smem>>>(gs, 0); break;
         case HX_STEP_RED_REFINE:   gipuma_red_planeRefine_cu<float><<<grid, block, smem>>>(gs, 0); break;
         case HX_STEP_COMPUTE_DISP: gipuma_compute_disp<<<grid16, block16>>>(gs); break;
+        case HX_STEP_BLACK_FUSED:  gipuma_black_cu<float><<<grid, block, smem>>>(gs, 0); break;
+        case HX_STEP_RED_FUSED:    gipuma_red_cu<float><<<grid, block, smem>>>(gs, 0); break;
         default: break;
         }
         cudaEventRecord(e1);

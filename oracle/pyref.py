@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(_HERE, "_ref")
 
 (STEP_INIT, STEP_BLACK_CLOSE, STEP_BLACK_FAR, STEP_BLACK_REFINE,
- STEP_RED_CLOSE, STEP_RED_FAR, STEP_RED_REFINE, STEP_COMPUTE_DISP) = range(8)
+ STEP_RED_CLOSE, STEP_RED_FAR, STEP_RED_REFINE, STEP_COMPUTE_DISP, STEP_BLACK_FUSED, STEP_RED_FUSED) = range(10)
 
 
 class HxParams(C.Structure):
@@ -124,6 +124,14 @@ class Harness:
         if rc != 0:
             raise RuntimeError("hx_steps failed: %d" % rc)
         return n4, c, ms
+
+    def run_fused(self, scene, seed: int = 0xC0FFEE):
+        """runcuda() as the reference behaves when built without SMALLKERNEL (gipuma.cu:1906-1945): init, then per
+        iteration the fused 20-neighbour black and red kernels, then gipuma_compute_disp.  Returns (norm4, cost,
+        ms of the sweep span = everything after init)."""
+        seq = [STEP_INIT] + [STEP_BLACK_FUSED, STEP_RED_FUSED] * scene.params.iterations + [STEP_COMPUTE_DISP]
+        n4, c, ms = self.steps(scene, seq, seed=seed)
+        return n4, c, float(ms[1:].sum())
 
     def cost_eval(self, scene, planes: np.ndarray):
         prm, cams, imgs, sub = self._common(scene)

@@ -105,7 +105,7 @@ def test_color_every_kernel_of_one_iteration_vs_live_reference():
         ctx.init()
         m4, mc = ctx.get_state()
         assert bits_equal(m4, n4) == 0 and bits_equal(mc, c) == 0
-        ctx.set_option("cost_variant", 2)                 # the initialisation kernel's rounding, on its own planes
+        ctx.set_option("cost_variant", 3)                 # the initialisation kernel's rounding, on its own planes
         assert bits_equal(ctx.cost_eval(n4), c) == 0
         for step, (colour, mask) in zip(range(1, 7), [(0, 1), (0, 2), (0, 4), (1, 1), (1, 2), (1, 4)]):
             n4, c, _ = ref.steps(sc, [step], norm4=n4, cost=c, seed=99)

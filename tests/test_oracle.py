@@ -133,3 +133,33 @@ def test_color_restatement_reduces_to_gray_for_equal_channels(small_scene):
     b = Oracle(cs).cost_eval(planes, y0=4, y1=8)[4:8]
     assert np.all(np.abs(a - b) <= 2e-6 * np.maximum(1.0, a))
     assert a.std() > 0
+
+
+def test_oracle_fused_sweep_agrees_with_reference_decisions():
+    """The fused 20-neighbour kernel (gipuma.cu:1122-1351): same criterion as above on the fused golden fixture."""
+    import glob
+    import os
+    from conftest import GOLDEN_DIR
+    from gipuma_b200.golden import scene_from_arrays
+    from oracle import pyoracle
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, "fused_box*.npz")))
+    if not paths:
+        pytest.skip("no fused golden fixture")
+    z = dict(np.load(paths[0]))
+    sc = scene_from_arrays("fused", z)
+    o = pyoracle.Oracle(sc)
+    y0, y1 = 16, 32
+    pl, c = o.phase(z["init_norm4"], z["init_cost"], 0, 8, y0, y1)       # the 20 candidates, no refinement
+    ref4, init = z["black_norm4"], z["init_norm4"]
+    ys, xs = np.mgrid[y0:y1, 0:sc.cols]
+    black = ((xs + ys) & 1) == 0
+    offs = [(0, 0)] + list(zip([-1, -3, -5, 1, 3, 5, 0, 0, 0, 0, 0, 0, -1, 1, -1, 1, -2, -2, 2, 2],
+                               [0, 0, 0, 0, 0, 0, -1, -3, -5, 1, 3, 5, 2, 2, -2, -2, -1, 1, -1, 1]))
+    copied = np.zeros(black.shape, bool)
+    for dy, dx in offs:
+        yy = np.clip(ys + dy, 0, sc.rows - 1)
+        xx = np.clip(xs + dx, 0, sc.cols - 1)
+        copied |= np.all(ref4[ys, xs] == init[yy, xx], axis=-1)
+    sel = black & copied
+    agree = np.all(pl[ys, xs][sel] == ref4[ys, xs][sel], axis=-1)
+    assert sel.sum() > 50 and agree.mean() > 0.97

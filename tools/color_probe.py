@@ -29,7 +29,7 @@ def main():
         ctx.init()
         m4, mc = ctx.get_state()
         print("init planes diff %d  cost diff %d  (max abs %.3g)" % (nbits(m4, n4), nbits(mc, c), np.abs(mc - c).max()))
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             ctx.set_option("cost_variant", variant)
             e = ctx.cost_eval(n4)
             print("cost_eval variant %d: vs ref init cost %d, vs ref cost_eval %d" % (variant, nbits(e, c), nbits(e, rc)))

@@ -27,10 +27,41 @@ CASES = {
 }
 
 
+FUSED_CASES = {
+    # the fused 20-neighbour sweep (reference built without SMALLKERNEL): name: (config, rows, cols, views, iterations, box, n_best, colour)
+    "fused_box11_v4": (2, 64, 96, 4, 2, 11, 3, False),
+    "fused_color_box9_v3": (2, 64, 96, 3, 2, 9, 2, True),
+}
+
+
+def fused(out_dir, only):
+    for name, (cfg, rows, cols, views, iters, box, nbest, colour) in FUSED_CASES.items():
+        if only and name not in only:
+            continue
+        sc = S.make_config(cfg, rows=rows, cols=cols, n_views=views, iterations=iters)
+        sc.params.box_hsize = sc.params.box_vsize = box
+        sc.params.n_best = nbest
+        if colour:
+            sc = S.colorize(sc)
+        h = pyref.Harness("ref")
+        seed = 0xC0FFEE
+        i_n4, i_c, _ = h.steps(sc, [pyref.STEP_INIT], seed=seed)
+        b_n4, b_c, _ = h.steps(sc, [pyref.STEP_BLACK_FUSED], norm4=i_n4, cost=i_c, seed=seed)
+        t_n4, t_c, _ = h.steps(sc, [pyref.STEP_RED_FUSED], norm4=b_n4, cost=b_c, seed=seed)
+        f_n4, f_c, _ = h.run_fused(sc, seed=seed)
+        arrs = scene_to_arrays(sc)
+        arrs.update(seed=np.uint64(seed), init_norm4=i_n4, init_cost=i_c, black_norm4=b_n4, black_cost=b_c,
+                    iter1_norm4=t_n4, iter1_cost=t_c, final_norm4=f_n4, final_cost=f_c)
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **arrs)
+        print(name, os.path.getsize(path), "bytes")
+
+
 def main():
     out_dir = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/golden"
     os.makedirs(out_dir, exist_ok=True)
     only = sys.argv[2:]
+    fused(out_dir, only)
     for name, (cfg, rows, cols, views, iters, box, nbest) in CASES.items():
         if only and name not in only:
             continue

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--cols", type=int, default=None)
     ap.add_argument("--views", type=int, default=None)
     ap.add_argument("--color", action="store_true", help="float4 images (-color_processing)")
+    ap.add_argument("--fused", action="store_true", help="the fused 20-neighbour kernels (reference built without SMALLKERNEL)")
     ap.add_argument("--save", type=str, default=None)
     ap.add_argument("--steps", action="store_true", help="also time each kernel of one iteration (hx_steps)")
     ap.add_argument("--repeat", type=int, default=1)
@@ -40,7 +41,11 @@ def main():
            "box": sc.params.box_hsize, "scene_s": round(t_scene, 2), "backend": h.backend, "runs": []}
     n4 = c = None
     for r in range(args.repeat):
-        n4, c, printed_s, wall_ms = h.run(sc)
+        if args.fused:
+            n4, c, ms = h.run_fused(sc)
+            printed_s, wall_ms = ms / 1000.0, ms
+        else:
+            n4, c, printed_s, wall_ms = h.run(sc)
         mpix = sc.rows * sc.cols * sc.params.iterations / 1e6 / printed_s if printed_s > 0 else float("nan")
         out["runs"].append({"printed_s": printed_s, "wall_ms": wall_ms, "mpixel_iters_per_s": mpix})
     if sc.gt_depth is not None:
