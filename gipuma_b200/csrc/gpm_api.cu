@@ -60,7 +60,9 @@ struct gpm_ctx {
     float* staging = nullptr;        // W*H floats, upload scratch
     cudaArray_t srcArr = nullptr;
     cudaTextureObject_t srcTex = 0;
-    cudaArray_t srcArr4 = nullptr;   // colour mode: layered RGBA32F + padded float4 reference + float4 staging
+    cudaArray_t srcArr4 = nullptr;   // colour mode: layered R32F, 3 channel planes per view (layer 3v + ch: an RGBA32F fetch costs
+                                     // 4.6x an R32F one on B200, profiles/r01_texbench.txt) + padded float4 reference + float4 staging
+    float* planar = nullptr;         // [3][H][W] split target
     cudaTextureObject_t srcTex4 = 0;
     float4* refpad4 = nullptr;
     float4* staging4 = nullptr;
@@ -320,7 +322,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->srcArr) cudaFreeArray(c->srcArr);
     if (c->srcTex4) cudaDestroyTextureObject(c->srcTex4);
     if (c->srcArr4) cudaFreeArray(c->srcArr4);
-    cudaFree(c->refpad4);  cudaFree(c->staging4);
+    cudaFree(c->refpad4);  cudaFree(c->staging4);  cudaFree(c->planar);
     if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
     if (c->gradArr) cudaFreeArray(c->gradArr);
     cudaFree(c->gradLin);  cudaFree(c->d_flag);
@@ -454,8 +456,9 @@ static int ensure_color(gpm_ctx* c, int want)
     if (c->color == -1) c->color = want;
     if (c->color != want) return fail(GPM_E_STATE, "a context holds either float or float4 images, not both");
     if (want == 1 && !c->srcArr4) {
-        cudaChannelFormatDesc d4 = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
-        CU(cudaMalloc3DArray(&c->srcArr4, &d4, make_cudaExtent(c->W, c->H, c->maxV), cudaArrayLayered));
+        cudaChannelFormatDesc d1 = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+        CU(cudaMalloc3DArray(&c->srcArr4, &d1, make_cudaExtent(c->W, c->H, 3 * (size_t)c->maxV), cudaArrayLayered));
+        CU(cudaMalloc(&c->planar, 3 * (size_t)c->W * c->H * sizeof(float)));
         cudaResourceDesc res;  memset(&res, 0, sizeof(res));
         res.resType = cudaResourceTypeArray;  res.res.array.array = c->srcArr4;
         cudaTextureDesc td;  memset(&td, 0, sizeof(td));
@@ -511,11 +514,16 @@ extern "C" int gpm_set_view_color(gpm_ctx* c, int v, const float* rgba, size_t p
     size_t pe = 0;
     rc = upload_image4(c, rgba, pitch_bytes, on_device, &d, &pe);
     if (rc) return rc;
+    {
+        dim3 b(32, 8), gr((c->W + 31) / 32, (c->H + 7) / 8);
+        k_split_channels<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->planar);
+        CU(cudaGetLastError());
+    }
     cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
-    m.srcPtr = make_cudaPitchedPtr(d, pe * sizeof(float4), c->W, c->H);
+    m.srcPtr = make_cudaPitchedPtr(c->planar, c->W * sizeof(float), c->W, c->H);
     m.dstArray = c->srcArr4;
-    m.dstPos = make_cudaPos(0, 0, v);
-    m.extent = make_cudaExtent(c->W, c->H, 1);
+    m.dstPos = make_cudaPos(0, 0, 3 * (size_t)v);
+    m.extent = make_cudaExtent(c->W, c->H, 3);
     m.kind = cudaMemcpyDeviceToDevice;
     CU(cudaMemcpy3DAsync(&m, c->stream));
     ViewCam& vc = c->h_cams[v];

@@ -552,6 +552,16 @@ __global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict
     planes[center] = o;
 }
 
+// Colour source views are sampled from three R32F planes (layer 3v + channel) instead of one RGBA32F layer.
+__global__ void k_split_channels(const float4* __restrict__ in, size_t pitch_elems, int W, int H, float* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4 p = in[(size_t)y * pitch_elems + x];
+    const size_t plane = (size_t)W * H, o = (size_t)y * W + x;
+    out[o] = p.x;  out[plane + o] = p.y;  out[2 * plane + o] = p.z;
+}
+
 // G[x,y] = (I[clamp(x+1),y] - I[clamp(x-1),y],  I[x,clamp(y+1)] - I[x,clamp(y-1)]) for the packed sampling mode, and a flag
 // that stays 1 only if every pixel is an integer in [0, 255] (the exactness condition of that mode).
 __global__ void k_make_gradients(const float* __restrict__ img, size_t pitch_floats, int W, int H, float2* __restrict__ out,
