@@ -85,11 +85,22 @@ def dist_env():
     return rank, world, local
 
 
-def make_scene(config: int, rank: int):
+def make_scene(config: int, rank: int, color: bool = False):
     from gipuma_b200 import scene as S
     # every rank gets its own reference view: another rendered surface / texture seed (and, for the DTU
     # configurations, the geometry of the same rig)
-    return S.make_config(config, seed=1234 + 17 * rank)
+    sc = S.make_config(config, seed=1234 + 17 * rank)
+    return S.colorize(sc) if color else sc
+
+
+def variant_suffix(args):
+    """Non-default modes of the path (both arms run the same one): float4 images, fused 20-neighbour sweep."""
+    out = ""
+    if args.color:
+        out += ", -color_processing (float4 images)"
+    if args.neighbours == 20:
+        out += ", fused 20-neighbour sweep (reference built without SMALLKERNEL)"
+    return out
 
 
 def algorithmic_bytes_per_sweep_launch(W, H, V):
@@ -99,9 +110,10 @@ def algorithmic_bytes_per_sweep_launch(W, H, V):
     return (W * H // 2) * (40 + 128 + 146) + (1 + V) * W * H * 4
 
 
-def cpu_baseline(sc, budget_s: float = 15.0) -> dict:
+def cpu_baseline(sc, budget_s: float = 15.0, neighbours: int = 8) -> dict:
     from oracle import pyoracle
     o = pyoracle.Oracle(sc)
+    threads = o.set_threads(len(os.sched_getaffinity(0)))       # all host cores this process may use (rows are independent)
     rng = np.random.default_rng(0)
     H, W = sc.rows, sc.cols
     pl = np.zeros((H, W, 4), np.float32)
@@ -109,31 +121,37 @@ def cpu_baseline(sc, budget_s: float = 15.0) -> dict:
     pl[..., 3] = sc.gt_depth * rng.uniform(0.9, 1.1, size=(H, W)).astype(np.float32)
     y0 = H // 2
     t0 = time.perf_counter()
-    c = o.cost_eval(pl, y0, y0 + 1, init_radius=True)          # calibrate: one row of initial costs
-    t_row = time.perf_counter() - t0
-    evals_per_px_iter = 2 * (8 + 3)                              # hypotheses per pixel-iteration (E = 8 + S, S = 3 on DTU)
-    rows = int(max(1, min(H // 2, budget_s / max(1e-6, t_row * evals_per_px_iter / 2))))
+    c = o.cost_eval(pl, y0, y0 + threads, init_radius=True)    # calibrate: one row of initial costs per thread
+    t_row = (time.perf_counter() - t0) / threads
+    evals_per_px_iter = 2 * (neighbours + 3)                     # hypotheses per pixel-iteration (E = 8 + S, S = 3 on DTU)
+    rows = int(max(threads, min(H // 2, budget_s / max(1e-6, t_row * evals_per_px_iter / 2))))
     cost = np.full((H, W), 50.0, np.float32)
     cost[y0:y0 + rows] = o.cost_eval(pl, y0, y0 + rows)[y0:y0 + rows]
     t0 = time.perf_counter()
-    o.sweep(pl, cost, 1, y0, y0 + rows)
+    if neighbours == 20:                                         # fused kernel: 20 candidates + refinement per colour
+        for colour in (0, 1):
+            pl, cost = o.phase(pl, cost, colour, 8 | 4, y0, y0 + rows)
+    else:
+        o.sweep(pl, cost, 1, y0, y0 + rows)
     dt = time.perf_counter() - t0
-    return {"value": rows * W * 1 / 1e6 / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "1 iteration over rows [%d,%d) of the same %dx%d / %d-view workload (%.1f s, single thread, host has %d cores)"
-                      % (y0, y0 + rows, W, H, sc.n_views, dt, os.cpu_count() or 0)}
+    return {"value": rows * W * 1 / 1e6 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "1 iteration over rows [%d,%d) of the same %dx%d / %d-view workload (%.1f s on %d OpenMP thread(s), host has %d cores)"
+                      % (y0, y0 + rows, W, H, sc.n_views, dt, threads, os.cpu_count() or 0)}
 
 
 def run_ours(args, rank, world, local):
     import torch
     from gipuma_b200 import api
     torch.cuda.set_device(local)
-    sc = make_scene(args.config, rank)
+    sc = make_scene(args.config, rank, args.color)
     W, H, V, iters = sc.cols, sc.rows, sc.n_views, sc.params.iterations
     pinned = torch.from_numpy(np.ascontiguousarray(sc.images)).pin_memory()
     out4 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     outc = torch.empty((H, W), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
     ctx = api.Context(W, H, V, device=local)
+    if args.neighbours != 8:
+        ctx.set_option("neighbours", args.neighbours)
     imgs = [pinned[i] for i in range(pinned.shape[0])]
 
     def upload():
@@ -204,12 +222,12 @@ def run_ours(args, rank, world, local):
         "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[%d]: %s, %dx%d, %d source views, %d iterations, blocksize %d, n_best %d"
-                               % (args.config - 1, sc.name, W, H, V, iters, sc.params.box_hsize, sc.params.n_best),
+                               % (args.config - 1, sc.name, W, H, V, iters, sc.params.box_hsize, sc.params.n_best) + variant_suffix(args),
                    "parallelism": "reference-view batch: %d independent reference view(s), one per GPU, no collective" % world,
                    "timed_span": "first sweep kernel .. end of final depth/normal kernel (reference's own span, init excluded)",
                    "l2": "flushed between timed steps (256 MiB write)", "rng": "seed 0xC0FFEE, reference zero-state refinement RNG"},
         "value_incl_init": units / (step_ms / 1e3),
-        "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int((1 + V) * W * H * 4),
+        "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.numel() * 4),
                 "d2h_bytes_per_step": int(W * H * 20), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -227,7 +245,7 @@ def run_ours(args, rank, world, local):
         "clocks": clocks,
     }
     try:
-        line["cpu_baseline"] = cpu_baseline(sc)
+        line["cpu_baseline"] = cpu_baseline(sc, neighbours=args.neighbours)
     except Exception as e:      # noqa: BLE001
         line["cpu_baseline"] = {"error": repr(e)}
     return line
@@ -240,20 +258,26 @@ def run_reference(args, rank, world, local):
     import torch
     from oracle import pyref
     torch.cuda.set_device(local)
-    sc = make_scene(args.config, 0)
+    sc = make_scene(args.config, 0, args.color)
     W, H, V, iters = sc.cols, sc.rows, sc.n_views, sc.params.iterations
     try:
         h = pyref.Harness("ref64" if V > 32 else "ref")
     except Exception as e:      # noqa: BLE001
         return {"impl": "reference", "unavailable": "pinned reference build missing: %r" % (e,)}
     sampler = ClockSampler(local)
+    def run_once():
+        if args.neighbours == 20:                     # the kernels a reference built without SMALLKERNEL launches
+            _, _, ms = h.run_fused(sc)
+            return ms / 1e3
+        return h.run(sc)[2]
+
     for _ in range(args.warmup):
-        h.run(sc)
+        run_once()
     sampler.start()
     printed = wall = 0.0
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        _, _, printed_s, _ = h.run(sc)
+        printed_s = run_once()
         wall += time.perf_counter() - t0
         printed += printed_s
     clocks = sampler.finish()
@@ -264,7 +288,7 @@ def run_reference(args, rank, world, local):
         "warmup": args.warmup, "ms_per_step": printed * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[%d]: %s, %dx%d, %d source views, %d iterations, blocksize %d, n_best %d"
-                               % (args.config - 1, sc.name, W, H, V, iters, sc.params.box_hsize, sc.params.n_best),
+                               % (args.config - 1, sc.name, W, H, V, iters, sc.params.box_hsize, sc.params.n_best) + variant_suffix(args),
                    "parallelism": "1 reference view on rank 0 (the reference is single-GPU, main.cpp:658-692)",
                    "timed_span": "the reference's own printed 'Total time needed for computation' (gipuma.cu:1908-1952)",
                    "build": "unmodified gipuma.cu, nvcc 12.9 -O3 --use_fast_math sm_100a, pins P1/P2 by macro (oracle/build_ref.sh)"},
@@ -283,6 +307,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--color", action="store_true", help="float4 images (the reference's -color_processing)")
+    ap.add_argument("--neighbours", type=int, default=8, choices=[8, 20],
+                    help="20: the fused sweep of a reference built without SMALLKERNEL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local = dist_env()

@@ -16,9 +16,12 @@
  * curand_init's XORWOW skip-ahead (curand_kernel.h) is not restated: initial planes are an input here (the
  * XORWOW stream itself and everything computed from it is restated, see gpo_random_plane).
  *
- * Build: gcc -O2 -fPIC -shared -o oracle/libgipuma_oracle.so oracle/gipuma_oracle.c -lm
+ * Build: gcc -O2 -fopenmp -fPIC -shared -o oracle/libgipuma_oracle.so oracle/gipuma_oracle.c -lm   (oracle/Makefile)
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -41,6 +44,19 @@ typedef struct gpo_scene {
  * 4th unused, as main.cpp:560-605 uploads them. */
 static int g_color = 0;
 void gpo_set_color(int on) { g_color = on != 0; }
+
+/* Rows of one colour are independent (a colour only reads the other colour's planes), and so are cost evaluations:
+ * the row loops below run on `g_threads` OpenMP threads (default 1; results do not depend on it). */
+static int g_threads = 1;
+void gpo_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+int gpo_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 /* ---- texture unit model: tex2D<float>(tex, x, y), Linear filter, clamp, unnormalised (main.cpp:642-648) ---- */
 static float texel(const float* img, int W, int H, int i, int j)
@@ -299,6 +315,7 @@ int gpo_cost_eval(int W, int H, int V, const gpm_params* prm, const gpm_camera* 
     gpo_scene s;
     make_scene(&s, W, H, V, prm, ref, views, ref_img, view_imgs);
     const int rad = init_radius ? prm->box_hsize / 2 : (prm->box_hsize - 1) / 2;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_threads)
     for (int y = y0; y < y1; y++)
         for (int x = 0; x < W; x++)
             cost[(size_t)y * W + x] = multiview_cost(&s, x, y, planes + 4 * ((size_t)y * W + x), rad);
@@ -332,6 +349,7 @@ int gpo_phase(int W, int H, int V, const gpm_params* prm, const gpm_camera* ref,
     gpo_scene s;
     make_scene(&s, W, H, V, prm, ref, views, ref_img, view_imgs);
     const int rad = (prm->box_hsize - 1) / 2;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_threads)
     for (int py = y0; py < y1; py++) {
         for (int px = 0; px < W; px++) {
             if (((px + py) & 1) != colour) continue;

@@ -19,7 +19,7 @@ LIB = os.path.join(_HERE, "libgipuma_oracle.so")
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "gipuma_oracle.c")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off",
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off",
                                "-o", LIB, src, "-lm"])
     return LIB
 
@@ -48,6 +48,12 @@ class Oracle:
         self.lib.gpo_tex2d.restype = C.c_float
         self.lib.gpo_random_plane.argtypes = [C.POINTER(GpmParams), C.POINTER(GpmCamera), C.c_int, C.c_int,
                                               C.POINTER(C.c_uint32), fp]
+
+    def set_threads(self, n: int) -> int:
+        """OpenMP threads for the row loops (results are independent of it); returns the number in effect."""
+        n = max(1, min(int(n), int(self.lib.gpo_max_threads())))
+        self.lib.gpo_set_threads(n)
+        return n
 
     def _common(self):
         self.lib.gpo_set_color(int(self.ref_img.ndim == 3))          # [H, W, 4] images: the float4 path

@@ -163,3 +163,24 @@ def test_oracle_fused_sweep_agrees_with_reference_decisions():
     sel = black & copied
     agree = np.all(pl[ys, xs][sel] == ref4[ys, xs][sel], axis=-1)
     assert sel.sum() > 50 and agree.mean() > 0.97
+
+
+def test_oracle_results_do_not_depend_on_the_thread_count(small_scene):
+    """Rows of one colour are independent, so the OpenMP row loops (used by bench.py's cpu_baseline) change nothing."""
+    from oracle.pyoracle import Oracle
+    sc = small_scene
+    o = Oracle(sc)
+    planes = np.zeros((sc.rows, sc.cols, 4), np.float32)
+    planes[..., 2] = -1.0
+    planes[..., 3] = sc.gt_depth
+    y0, y1 = 8, 16
+    o.set_threads(1)
+    c1 = o.cost_eval(planes, y0, y1)
+    p1, k1 = o.sweep(planes, c1, 1, y0, y1)
+    n = o.set_threads(4)
+    c4 = o.cost_eval(planes, y0, y1)
+    p4, k4 = o.sweep(planes, c4, 1, y0, y1)
+    o.set_threads(1)
+    assert n >= 1
+    assert np.array_equal(c1.view(np.uint32), c4.view(np.uint32))
+    assert np.array_equal(p1.view(np.uint32), p4.view(np.uint32)) and np.array_equal(k1.view(np.uint32), k4.view(np.uint32))
