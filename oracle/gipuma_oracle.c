@@ -156,9 +156,15 @@ static void homography(const gpm_camera* ref, const gpm_camera* to, const float 
 /* ---- photo-consistency cost --------------------------------------------------------------------------- */
 /* pmCost_shared / pmCost + pmCostComputation(_shared) + weight_cu: gipuma.cu:585-680, 455-518, 223-320, 186-193.
  * The reference window is read with clamp addressing, exactly what the shared tile / texture deliver. */
+/* Diagnostics (tools/prune_study.py): when set, view_cost() also stores every sample's term w*dis, [v][sample] with
+ * row length g_tap_stride, in window order. */
+static float* g_tap = NULL;
+static int g_tap_stride = 0;
+
 static float view_cost(const gpo_scene* s, int v, int px, int py, const float n[4], int rad)
 {
     const gpm_params* p = s->prm;
+    int tap_k = 0;
     float H[9];
     homography(s->ref, &s->views[v], n, H);
     const float* L = s->ref_img;
@@ -182,6 +188,7 @@ static float view_cost(const gpo_scene* s, int v, int px, int py, const float n[
             const float gradDis = fminf((fabsf(gx1 - gx2) + fabsf(gy1 - gy2)) * 0.0625f, p->tau_gradient);              /* :267 */
             const float colDis = fminf(colDiff, p->tau_color);                                                          /* :271 */
             cost = cost + w * ((1.f - p->alpha) * colDis + p->alpha * gradDis);                                         /* :272-274, :674 */
+            if (g_tap) g_tap[(size_t)v * g_tap_stride + tap_k++] = w * ((1.f - p->alpha) * colDis + p->alpha * gradDis);
         }
     }
     return cost;
@@ -438,6 +445,19 @@ int gpo_sweep(int W, int H, int V, const gpm_params* prm, const gpm_camera* ref,
             for (int ph = 1; ph <= 4; ph <<= 1)
                 gpo_phase(W, H, V, prm, ref, views, ref_img, view_imgs, planes, cost, colour, ph, y0, y1);
     return 0;
+}
+
+/* Combined cost of one plane at one pixel plus every sample term of every view (diagnostics). */
+float gpo_multiview_terms(int W, int H, int V, const gpm_params* prm, const gpm_camera* ref, const gpm_camera* views,
+                          const float* ref_img, const float* const* view_imgs, int px, int py, const float* plane,
+                          float* terms, int stride)
+{
+    gpo_scene s;
+    make_scene(&s, W, H, V, prm, ref, views, ref_img, view_imgs);
+    g_tap = terms;  g_tap_stride = stride;
+    const float c = multiview_cost(&s, px, py, plane, (prm->box_hsize - 1) / 2);
+    g_tap = NULL;
+    return c;
 }
 
 float gpo_tex2d(const float* img, int W, int H, float x, float y) { return tex2d(img, W, H, x, y); }

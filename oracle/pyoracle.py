@@ -19,8 +19,10 @@ LIB = os.path.join(_HERE, "libgipuma_oracle.so")
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "gipuma_oracle.c")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off",
-                               "-o", LIB, src, "-lm"])
+        base = ["gcc", "-O2", "-fPIC", "-shared", "-fno-fast-math", "-ffp-contract=off", "-o", LIB, src, "-lm"]
+        # OpenMP row loops where the toolchain has libgomp (bench.py's multi-core CPU baseline); scalar otherwise
+        if subprocess.call(base[:2] + ["-fopenmp"] + base[2:], stderr=subprocess.DEVNULL) != 0:
+            subprocess.check_call(base)
     return LIB
 
 
@@ -100,3 +102,17 @@ class Oracle:
         out = np.zeros(4, dtype=np.float32)
         self.lib.gpo_random_plane(C.byref(self.prm), C.byref(self.ref), px, py, st, self._fp(out))
         return out
+
+    def plane_depth(self, plane, px, py) -> float:
+        """getDisparity_cu / getDepthFromPlane3_cu (gipuma.cu:694-715): depth of the plane (n, d) along the ray of pixel (px, py)."""
+        p = np.ascontiguousarray(plane, dtype=np.float32)
+        self.lib.gpo_plane_depth.restype = C.c_float
+        self.lib.gpo_plane_depth.argtypes = [C.POINTER(GpmCamera), C.POINTER(C.c_float), C.c_int, C.c_int]
+        return float(self.lib.gpo_plane_depth(C.byref(self.ref), self._fp(p), px, py))
+
+    def plane_d(self, normal, px, py, depth) -> float:
+        """getD_cu (gipuma.cu:96-111): d of the plane with this normal through the point at `depth` on the pixel's ray."""
+        n = np.ascontiguousarray(normal[:3], dtype=np.float32)
+        self.lib.gpo_plane_d.restype = C.c_float
+        self.lib.gpo_plane_d.argtypes = [C.POINTER(GpmCamera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float]
+        return float(self.lib.gpo_plane_d(C.byref(self.ref), self._fp(n), px, py, depth))
