@@ -83,6 +83,7 @@ struct gpm_ctx {
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
     int opt_cost_variant = -1, opt_packed = 0, opt_memo = 1;
+    int opt_shard_async = 0;                     // 1: gpm_shard_eval / gpm_shard_accept only enqueue on gpm_stream()
     int opt_neighbours = 8;                      // 20: the reference's fused kernel (built when SMALLKERNEL is not defined)
     int opt_site[21];                            // diagnostics: override the fused kernel's call-site variants (-1 = table)
     int smem_optin = 0, num_sms = 148;
@@ -764,11 +765,14 @@ extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev
     int rc = shard_common(c, stage, P);
     if (rc) return rc;
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
+    int split = 1;                                        // at least ~8 waves of blocks, as in launch_colour
+    while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
+    grid.z = split;
     (P.color ? k_shard_eval<false, true> : (P.packed ? k_shard_eval<true, false> : k_shard_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost,
                                                                           c->prov, c->dispbuf, c->candbuf, c->canddepth, c->seen, c->memo_mask, colour, stage, xchg_dev);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));       // the caller's collective runs on another stream
+    if (!c->opt_shard_async) CU(cudaStreamSynchronize(c->stream));       // the caller's collective may run on another stream
     return GPM_OK;
 }
 
@@ -784,7 +788,7 @@ extern "C" int gpm_shard_accept(gpm_ctx* c, int colour, int stage, const float* 
                                             gathered_dev, world);
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
+    if (!c->opt_shard_async) CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
 
@@ -854,6 +858,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     }
     else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
+    else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;
 }

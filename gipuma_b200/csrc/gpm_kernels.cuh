@@ -371,7 +371,11 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
     const float inf = __int_as_float(0x7f800000);
     // stage 0 visits every pixel (both colours, like gipuma_init_cu2); the others one colour
     const int npix = (stage == 0) ? GPM_TILE * GPM_TILE : GPM_TILE * GPM_TILE / 2;
-    for (int idx = warp; idx < npix; idx += P.nwarps) {
+    // gridDim.z slices of the tile's pixel list, as in k_sweep: small images would otherwise leave most SMs idle in the
+    // last wave (640x480 = 300 tiles on 148 SMs)
+    const int per_slice = (npix + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int idx_end = min(npix, ((int)blockIdx.z + 1) * per_slice);
+    for (int idx = (int)blockIdx.z * per_slice + (int)warp; idx < idx_end; idx += P.nwarps) {
         int px, py;
         if (stage == 0) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
         else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }

@@ -164,6 +164,10 @@ class ViewShardRunner:
             ctx.set_view(v, np.ascontiguousarray(scene.images[idx]), scene.cameras[idx])
         ctx.set_num_views(len(self.local))
         ctx.set_rng(seed)
+        # every stage is enqueued on the context's own stream — kernels and the NCCL all-gather alike — so that the
+        # 2 x (1 + S) x iterations stages need no host synchronisation in between
+        ctx.set_option("shard_async", 1)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", device))
         self.dev = torch.device("cuda", device)
         self.n_stages = ctx.shard_num_stages()
         self.xchg = {}
@@ -180,24 +184,24 @@ class ViewShardRunner:
         loc, gat = self.xchg[self.stage_floats[stage]]
         self.ctx.shard_eval(colour, stage, loc)
         if self.world > 1:
-            dist.all_gather_into_tensor(gat, loc, group=self.group)
-            self.torch.cuda.synchronize(self.dev)
+            dist.all_gather_into_tensor(gat, loc, group=self.group)     # ordered after shard_eval: same (current) stream
             self.collectives += 1
         else:
             gat.copy_(loc)
-            self.torch.cuda.synchronize(self.dev)
         self.ctx.shard_accept(colour, stage, gat, self.world)
 
     def run(self):
         """runcuda() with sharded views: returns (norm4, cost) like Context.get_state after gpm_run."""
         ctx = self.ctx
-        ctx.init_planes()                                   # identical on all ranks (same seed)
-        self._stage(0, 0)                                   # initial costs over all views
-        for _ in range(self.scene.params.iterations):
-            for colour in (0, 1):
-                for stage in range(1, self.n_stages):
-                    self._stage(colour, stage)
-        ctx.finalize()
+        with self.torch.cuda.stream(self.stream):
+            ctx.init_planes()                               # identical on all ranks (same seed)
+            self._stage(0, 0)                               # initial costs over all views
+            for _ in range(self.scene.params.iterations):
+                for colour in (0, 1):
+                    for stage in range(1, self.n_stages):
+                        self._stage(colour, stage)
+            ctx.finalize()
+        self.stream.synchronize()
         return ctx.get_state()
 
     def close(self):

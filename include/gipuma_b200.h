@@ -149,6 +149,8 @@ int gpm_reset_stats(gpm_ctx* ctx);
  * known to reject (exact); "cost_variant" (-1 = auto): which of the reference binary's rounding variants gpm_cost_eval
  * reproduces: bit 0 = x-term first (float: 1 in the propagation kernels, 0 at init / refinement; float4: 0 in
  * all six sweep kernels), bit 1 = float4 gradient folding (float4 initialisation = 3); auto = the propagation kernels' form;
+ * "shard_async" (0): 1 makes gpm_shard_eval / gpm_shard_accept return after enqueueing on gpm_stream() — run the collective
+ * on that stream (or order it with events) instead of paying two host synchronisations per stage;
  * "neighbours" (8): 20 selects the reference's fused sweep — the kernels it launches when built without SMALLKERNEL
  * (gipuma.cu:1122-1351, 1913-1940): 12 axial + 8 knight-move neighbours, then refinement, one launch per colour; bit-exact
  * like the default (view sharding stays 8-neighbour only).

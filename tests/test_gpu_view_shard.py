@@ -81,6 +81,19 @@ def test_view_shard_color_images():
         assert bits_equal(n4, single.norm4) == 0 and bits_equal(c, single.c) == 0
 
 
+def test_view_shard_runner_single_rank_stream_ordered():
+    """multigpu.ViewShardRunner at world size 1: every stage enqueued on the context's stream (shard_async), no host
+    synchronisation in between — must still equal the fused single-context run bit for bit."""
+    from gipuma_b200 import api, multigpu as M, scene as S
+    sc = S.make_config(4, rows=96, cols=128, n_views=12, iterations=2, seed=557)
+    single, _, _ = api.runcuda(sc, seed=0xC0FFEE)
+    run = M.ViewShardRunner(sc, 0, 1)
+    for _ in range(2):                                     # twice: the second run re-uses buffers and memo state
+        n4, c = run.run()
+        assert bits_equal(n4, single.norm4) == 0 and bits_equal(c, single.c) == 0
+    run.close()
+
+
 def test_view_shard_refuses_other_combinations():
     import torch
     from gipuma_b200 import api, scene as S
