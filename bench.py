@@ -105,9 +105,9 @@ def variant_suffix(args):
 
 def algorithmic_bytes_per_sweep_launch(W, H, V):
     """one k_sweep launch = one colour (W*H/2 pixels): own plane+cost read and written (2*20 B),
-    8 neighbour planes (8*16 B), the memo of rejected work read (8*16 + 16 + 2 B; its writes are data dependent and not
+    8 neighbour planes (8*16 B), the memo of rejected work read (8*16 + 16 + 4 B; its writes are data dependent and not
     counted), and each image plane (reference + V sources) streamed once (4 B/pixel each)."""
-    return (W * H // 2) * (40 + 128 + 146) + (1 + V) * W * H * 4
+    return (W * H // 2) * (40 + 128 + 148) + (1 + V) * W * H * 4
 
 
 def cpu_baseline(sc, budget_s: float = 15.0, neighbours: int = 8) -> dict:
@@ -231,7 +231,7 @@ def run_ours(args, rank, world, local):
                 "d2h_bytes_per_step": int(W * H * 20), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": 449.7e6,
+                     "traffic": 453.3e6,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "kernel": "gpm::k_sweep", "avg_launch_ms": avg_launch_ms,
                      "binding_unit": {"name": "l1tex__data_pipe_tex_wavefronts", "frac_of_peak": 0.950,
