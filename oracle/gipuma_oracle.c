@@ -13,8 +13,9 @@
  * against golden outputs of that build (tests/golden/); this C restatement is pinned to the compiled reference
  * within tolerance by tests/test_oracle_vs_golden.py (cost level: |dc| <= 2e-3 * max(1, c)) and serves as the
  * readable specification, the function-level checker, and the CPU timing baseline.
- * curand_init's XORWOW skip-ahead (curand_kernel.h) is not restated: initial planes are an input here (the
- * XORWOW stream itself and everything computed from it is restated, see gpo_random_plane).
+ * Third-party arithmetic on the path, cuRAND's XORWOW (CUDA toolkit 12.9 curand_kernel.h): curand_init's seed scrambling and
+ * skip-ahead, the generator step and curand_uniform are restated here too (gpo_curand_init, gpo_init_planes) and pinned to
+ * known answers computed by the toolkit header itself on the host (tests/golden/xorwow_init_kat.json).
  *
  * Build: gcc -O2 -fopenmp -fPIC -shared -o oracle/libgipuma_oracle.so oracle/gipuma_oracle.c -lm   (oracle/Makefile)
  */
@@ -303,6 +304,87 @@ void gpo_random_plane(const gpm_params* p, const gpm_camera* ref, int px, int py
     const float depth = ref->f * ref->baseline / disp;                                  /* :1031 */
     out[0] = n[0]; out[1] = n[1]; out[2] = n[2];
     out[3] = plane_d(ref, n, px, py, depth);                                            /* :1034 */
+}
+
+/* ---- curand_init(seed, subsequence, offset) for XORWOW — CUDA toolkit 12.9, curand_kernel.h:772-856 ---------------------
+ * The reference calls curand_init(seed, p.y, p.x, &state) per pixel (gipuma.cu:1019).  cuRAND defines it as: scramble the
+ * seed into (v[0..4], d) (:836-847); advance by `subsequence` * 2^67 steps (skipahead_sequence); advance by `offset` steps
+ * (skipahead; d += 362437 * offset).  The toolkit does the jumps with precomputed matrices; the restatement below builds the
+ * 2^67-step matrix itself: the five v words evolve linearly over GF(2) (the step of curand(), :863-871, without the Weyl
+ * counter d), so one step is a 160 x 160 bit matrix M and the subsequence jump is M^(2^67), 67 squarings.  d is untouched by
+ * subsequence jumps (2^67 * 362437 = 0 mod 2^32, :697, :736).  Pinned by tests/golden/xorwow_init_kat.json, generated from
+ * the toolkit header compiled for the host (tools/make_xorwow_kat.cu). */
+static void xorwow_linear_step(uint32_t v[5])
+{
+    const uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+typedef struct { uint32_t col[160][5]; } xorwow_mat;         /* column j = image of basis vector e_j */
+static void xorwow_matvec(const xorwow_mat* m, const uint32_t in[5], uint32_t out[5])
+{
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int j = 0; j < 160; j++)
+        if ((in[j >> 5] >> (j & 31)) & 1u)
+            for (int k = 0; k < 5; k++) r[k] ^= m->col[j][k];
+    memcpy(out, r, sizeof(r));
+}
+static const xorwow_mat* xorwow_sequence_matrix(void)        /* M^(2^67), built once */
+{
+    static xorwow_mat a, b;
+    static int ready = 0;
+    if (!ready) {
+        for (int j = 0; j < 160; j++) {
+            uint32_t e[5] = {0, 0, 0, 0, 0};
+            e[j >> 5] = 1u << (j & 31);
+            xorwow_linear_step(e);
+            memcpy(a.col[j], e, sizeof(e));
+        }
+        for (int sq = 0; sq < 67; sq++) {                    /* a <- a * a */
+            for (int j = 0; j < 160; j++) xorwow_matvec(&a, a.col[j], b.col[j]);
+            a = b;
+        }
+        ready = 1;
+    }
+    return &a;
+}
+/* state6 = (v[0..4], d) after curand_init(seed, subsequence, offset) */
+void gpo_curand_init(uint64_t seed, uint64_t subsequence, uint64_t offset, uint32_t state6[6])
+{
+    const uint32_t s0 = (uint32_t)seed ^ 0xaad26b49u, s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;   /* curand_kernel.h:836-847 */
+    const uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
+    uint32_t v[5] = {123456789u + t0, 362436069u ^ t0, 521288629u + t1, 88675123u ^ t1, 5783321u + t0};
+    uint32_t d = 6615241u + t1 + t0;
+    const xorwow_mat* A = xorwow_sequence_matrix();
+    xorwow_mat P = *A, T;                                    /* v <- A^subsequence v by binary powers of A */
+    for (uint64_t n = subsequence; n; n >>= 1) {
+        if (n & 1) xorwow_matvec(&P, v, v);
+        if (n >> 1) { for (int j = 0; j < 160; j++) xorwow_matvec(&P, P.col[j], T.col[j]);  P = T; }
+    }
+    for (uint64_t k = 0; k < offset; k++) xorwow_linear_step(v);     /* offsets on this path are pixel columns: step them */
+    d += 362437u * (uint32_t)offset;
+    memcpy(state6, v, sizeof(v));
+    state6[5] = d;
+}
+/* gipuma_init_cu2's planes for the whole image (gipuma.cu:1019-1034): curand_init(seed, y, x) per pixel, then the draws of
+ * gpo_random_plane.  Row states by one subsequence jump per row, pixels of a row by single steps. */
+void gpo_random_plane(const gpm_params* p, const gpm_camera* ref, int px, int py, const uint32_t state[6], float out[4]);
+int gpo_init_planes(int W, int H, const gpm_params* prm, const gpm_camera* ref, uint64_t seed, float* planes)
+{
+    uint32_t row[6];
+    gpo_curand_init(seed, 0, 0, row);
+    const xorwow_mat* A = xorwow_sequence_matrix();
+    for (int y = 0; y < H; y++) {
+        uint32_t st[6];
+        memcpy(st, row, sizeof(st));
+        for (int x = 0; x < W; x++) {
+            gpo_random_plane(prm, ref, x, y, st, planes + 4 * ((size_t)y * W + x));
+            xorwow_linear_step(st);                            /* offset x + 1 */
+            st[5] += 362437u;
+        }
+        xorwow_matvec(A, row, row);                            /* subsequence y + 1 (d unchanged) */
+    }
+    return 0;
 }
 
 /* ---- entry points ---------------------------------------------------------------------------------------- */

@@ -116,3 +116,19 @@ class Oracle:
         self.lib.gpo_plane_d.restype = C.c_float
         self.lib.gpo_plane_d.argtypes = [C.POINTER(GpmCamera), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_float]
         return float(self.lib.gpo_plane_d(C.byref(self.ref), self._fp(n), px, py, depth))
+
+    def curand_init(self, seed: int, subsequence: int, offset: int) -> np.ndarray:
+        """XORWOW state (v[0..4], d) after curand_init(seed, subsequence, offset) — restated in gipuma_oracle.c."""
+        st = (C.c_uint32 * 6)()
+        self.lib.gpo_curand_init.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
+        self.lib.gpo_curand_init.restype = None
+        self.lib.gpo_curand_init(seed, subsequence, offset, st)
+        return np.array(list(st), dtype=np.uint32)
+
+    def init_planes(self, seed: int) -> np.ndarray:
+        """The random planes of gipuma_init_cu2 (gipuma.cu:1019-1034) for the whole image: curand_init(seed, y, x) per pixel."""
+        out = np.zeros((self.H, self.W, 4), dtype=np.float32)
+        self.lib.gpo_init_planes.argtypes = [C.c_int, C.c_int, C.POINTER(GpmParams), C.POINTER(GpmCamera), C.c_uint64,
+                                             C.POINTER(C.c_float)]
+        self.lib.gpo_init_planes(self.W, self.H, C.byref(self.prm), C.byref(self.ref), seed, self._fp(out))
+        return out

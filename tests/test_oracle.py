@@ -184,3 +184,45 @@ def test_oracle_results_do_not_depend_on_the_thread_count(small_scene):
     assert n >= 1
     assert np.array_equal(c1.view(np.uint32), c4.view(np.uint32))
     assert np.array_equal(p1.view(np.uint32), p4.view(np.uint32)) and np.array_equal(k1.view(np.uint32), k4.view(np.uint32))
+
+
+def test_curand_init_restatement_against_toolkit_known_answers(small_scene):
+    """curand_init(seed, subsequence, offset) for XORWOW, restated in the oracle (seed scrambling, 2^67-step subsequence
+    jumps by GF(2) matrix powers, offsets), against vectors computed by the CUDA toolkit's own curand_kernel.h on the host
+    (tools/make_xorwow_kat.cu -> tests/golden/xorwow_init_kat.json)."""
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle.pyoracle import Oracle
+    kat = json.load(open(os.path.join(GOLDEN_DIR, "xorwow_init_kat.json")))["vectors"]
+    o = Oracle(small_scene)
+    assert len(kat) > 400
+    for seed, sub, off, v0, v1, v2, v3, v4, d, r0, r1 in kat:
+        st = o.curand_init(seed, sub, off)
+        assert [int(x) for x in st] == [v0, v1, v2, v3, v4, d], (seed, sub, off)
+        # and the generator step (curand_kernel.h:863-874) from that state
+        v = [int(x) for x in st[:5]]
+        dd = int(st[5])
+        outs = []
+        for _ in range(2):
+            t = (v[0] ^ (v[0] >> 2)) & 0xFFFFFFFF
+            v = [v[1], v[2], v[3], v[4], ((v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1))) & 0xFFFFFFFF]
+            dd = (dd + 362437) & 0xFFFFFFFF
+            outs.append((v[4] + dd) & 0xFFFFFFFF)
+        assert outs == [r0, r1]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_initial_planes_match_compiled_reference(golden, name):
+    """gipuma_init_cu2's random planes (gipuma.cu:1019-1034) from the restated curand_init + XORWOW draws, against the
+    compiled reference's output (golden init_norm4).  Integer RNG stream exact; the plane arithmetic (sqrt, divisions)
+    is fast-math on the GPU, hence the tolerance; a Marsaglia rejection decided the other way would show as a gross
+    mismatch, so at most a handful of pixels may disagree."""
+    from oracle import pyoracle
+    sc, z = golden[name]
+    pl = pyoracle.Oracle(sc).init_planes(int(z["seed"]))
+    ref = z["init_norm4"]
+    err_n = np.abs(pl[..., :3] - ref[..., :3]).max(axis=-1)
+    err_d = np.abs(pl[..., 3] - ref[..., 3]) / np.maximum(1.0, np.abs(ref[..., 3]))
+    ok = (err_n < 1e-4) & (err_d < 1e-4)
+    assert ok.mean() > 0.999, (ok.mean(), err_n.max(), err_d.max())
