@@ -132,3 +132,14 @@ class Oracle:
                                              C.POINTER(C.c_float)]
         self.lib.gpo_init_planes(self.W, self.H, C.byref(self.prm), C.byref(self.ref), seed, self._fp(out))
         return out
+
+    def run(self, seed: int, fused: bool = False):
+        """runcuda() on the CPU (gipuma.cu:1825-1960): random planes, initial costs, `iterations` red/black sweeps
+        (fused = the 20-neighbour kernels of a build without SMALLKERNEL), gipuma_compute_disp.  Returns (norm4, cost)."""
+        pl = self.init_planes(seed)
+        c = self.cost_eval(pl, init_radius=True)
+        for _ in range(self.sc.params.iterations):
+            for colour in (0, 1):
+                for mask in ((8 | 4,) if fused else (1, 2, 4)):
+                    pl, c = self.phase(pl, c, colour, mask)
+        return self.finalize(pl, c), c
