@@ -548,7 +548,7 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (norm4) CU(cudaMemcpyAsync(c->planes, norm4, n * sizeof(float4), k, c->stream));
     if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
-    // provenance of the supplied costs is unknown (2) unless the caller vouches that they came from an
+    // provenance of the supplied costs is unknown (GPM_PROV_UNKNOWN) unless the caller vouches that they came from an
     // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
     CU(cudaMemsetAsync(c->prov, c->opt_trust_state ? (c->color == 1 ? 3 : 0) : GPM_PROV_UNKNOWN, n, c->stream));
     CU(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned), c->stream));

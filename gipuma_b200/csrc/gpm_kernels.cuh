@@ -174,7 +174,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
             float4 norm_now = planes[center];
             float cost_now = cost[center];
             float disp_now = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);   // :1530
-            // which rounding variant of the cost function produced cost_now: 0 = y-first (XFIRST false), 1 = x-first, 2 = unknown
+            // which rounding variant of the cost function produced cost_now: eval_plane's rt (0 = y-first, 1 = x-first, ...), 0xff = unknown
             int prov_now = prov[center];
 
             // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462);
