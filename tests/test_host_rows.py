@@ -58,3 +58,82 @@ def test_dmb_layout_and_roundtrip(tmp_path):
     assert struct.unpack("<4i", open(pn, "rb").read(16)) == (1, 5, 7, 3)       # writeDmbNormal :320-343
     with pytest.raises(api.GipumaError):
         api.read_dmb(str(tmp_path / "missing.dmb"))
+
+
+# ---- property tests (hypothesis) ----------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st      # noqa: E402
+
+
+def _random_rotation(rng):
+    q, r = np.linalg.qr(rng.normal(size=(3, 3)))
+    q = q * np.sign(np.diag(r))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(min_value=0, max_value=2 ** 31 - 1))
+def test_prepare_cameras_recovers_random_pinhole_rigs(seed):
+    """P = K [R | t] with random intrinsics (incl. skew) and poses: the C++ RQ restatement (cameraGeometryUtils.h:174-353) must
+    return an upper-triangular K with positive diagonal, a proper rotation, and K [R | t] must reproduce the re-based
+    projection; the reference camera comes out canonical."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 6))
+    Ps = []
+    for _ in range(n):
+        fx, fy = rng.uniform(500, 4000, 2)
+        K = np.array([[fx, rng.uniform(-2, 2), rng.uniform(200, 1500)], [0, fy, rng.uniform(200, 1200)], [0, 0, 1.0]])
+        R = _random_rotation(rng)
+        t = rng.uniform(-300, 300, 3)
+        Ps.append(rng.uniform(0.5, 2.0) * K @ np.hstack([R, t[:, None]]))            # arbitrary positive scale
+    cams = api.prepare_cameras(Ps)
+    for i, c in enumerate(cams):
+        K = np.array(c.K).reshape(3, 3)
+        R = np.array(c.R).reshape(3, 3)
+        assert abs(K[1, 0]) < 1e-3 and abs(K[2, 0]) < 1e-5 and abs(K[2, 1]) < 1e-5 and K[0, 0] > 0 and K[1, 1] > 0
+        assert K[2, 2] == pytest.approx(1.0, abs=1e-5)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-4) and np.linalg.det(R) == pytest.approx(1.0, abs=1e-3)
+        assert np.allclose(K @ np.array(c.K_inv).reshape(3, 3), np.eye(3), atol=1e-3)
+    R0 = np.array(cams[0].R).reshape(3, 3)
+    assert np.allclose(R0, np.eye(3), atol=1e-5) and np.allclose(np.array(cams[0].t), 0, atol=1e-2)
+    # relative pose preserved by the re-basing: R_i R_0^T of the inputs == R_i of the outputs
+    Rin = []
+    for P in Ps:
+        K, R, _ = S.decompose_projection(np.asarray(P, dtype=np.float64))[:3]
+        Rin.append(R)
+    for i in range(1, n):
+        assert np.allclose(np.array(cams[i].R).reshape(3, 3), Rin[i] @ Rin[0].T, atol=2e-3)
+
+
+@settings(max_examples=20, deadline=None)
+@given(rows=st.integers(1, 40), cols=st.integers(1, 40), ch=st.sampled_from([1, 3]), seed=st.integers(0, 2 ** 31 - 1))
+def test_dmb_roundtrip_any_shape(rows, cols, ch, seed):
+    import os
+    import tempfile
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(rows, cols) if ch == 1 else (rows, cols, ch)).astype(np.float32)
+    p = os.path.join(tempfile.mkdtemp(prefix="gpm_dmb_"), "x.dmb")
+    api.write_dmb(p, a)
+    raw = open(p, "rb").read()
+    assert len(raw) == 16 + 4 * rows * cols * ch and struct.unpack("<4i", raw[:16]) == (1, rows, cols, ch)
+    assert np.array_equal(api.read_dmb(p), a)
+    open(p, "wb").write(raw[:-4])                                                    # truncated payload
+    with pytest.raises(api.GipumaError):
+        api.read_dmb(p)
+
+
+def test_select_views_is_monotone_in_max_views_and_respects_the_angle_window():
+    Ps = S._dtu_Ps()
+    cams = api.prepare_cameras(Ps)
+    prev = []
+    for mv in (1, 3, 9, 20, 64):
+        sub, _ = api.select_views(cams, 1600, 1200, 10.0, 30.0, mv)
+        assert len(sub) <= mv and len(set(sub)) == len(sub) and 0 not in sub
+        assert sub[:len(prev)] == prev                                                # deterministic prefix order
+        prev = sub
+    none, _ = api.select_views(cams, 1600, 1200, 89.0, 90.0, 9)                       # nobody that oblique on the DTU rig
+    assert none == []
+    ang = S.view_angles(S.prepare_cameras(Ps), 1600, 1200)
+    for i in prev:
+        assert 10.0 <= ang[i] <= 30.0
