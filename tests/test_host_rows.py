@@ -136,4 +136,4 @@ def test_select_views_is_monotone_in_max_views_and_respects_the_angle_window():
     assert none == []
     ang = S.view_angles(S.prepare_cameras(Ps), 1600, 1200)
     for i in prev:
-        assert 10.0 <= ang[i] <= 30.0
+        assert 10.0 <= np.degrees(ang[i]) <= 30.0
