@@ -82,7 +82,7 @@ struct gpm_ctx {
     unsigned long long* d_stats = nullptr;
     unsigned long long launches = 0;
     int opt_prune = 1, opt_dedupe = 1, opt_trust_state = 0, opt_nwarps = 0, opt_stats = 1;
-    int opt_cost_variant = -1, opt_packed = 0, opt_memo = 1;
+    int opt_cost_variant = -1, opt_packed = 0, opt_memo = 1, opt_quadperm = 1;
     int opt_shard_async = 0;                     // 1: gpm_shard_eval / gpm_shard_accept only enqueue on gpm_stream()
     int opt_neighbours = 8;                      // 20: the reference's fused kernel (built when SMALLKERNEL is not defined)
     int opt_site[21];                            // diagnostics: override the fused kernel's call-site variants (-1 = table)
@@ -126,6 +126,35 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
             P.round_end[r++] = (unsigned char)P.ns;
         }
         P.nrounds = r;
+    }
+    // lane -> sample table of each round.  The texture unit filters a warp's fetches one hardware quad (lanes 4q..4q+3) at a
+    // time and is fastest when a quad's four footprints form a compact 2x2 block (profiles/r02_texshape.txt): with
+    // "quadperm" the samples of a round are dealt to the lanes as 2x2 blocks (x offset i, i+2; y offset j, j+2) where the
+    // round contains them, leftovers in window order.  Only WHICH lane evaluates a sample changes; the per-view FMA chain
+    // still consumes the dissimilarities in the reference's order.
+    P.quadperm = c->opt_quadperm;
+    {
+        int s0 = 0;
+        for (int r = 0; r < P.nrounds; r++) {
+            const int s1 = P.round_end[r], len = s1 - s0;
+            unsigned char* row = P.perm[r];
+            for (int l = 0; l < 32; l++) row[l] = (unsigned char)(l < len ? l : 0);
+            if (P.quadperm && len >= 4 && len <= 32) {
+                bool used[32] = {false};
+                int n = 0;
+                for (int k = 0; k < len; k++) {
+                    if (used[k]) continue;
+                    const int s = s0 + k, jj = s % P.nside;
+                    const int kr = k + P.nside, kd = k + 1, kx = k + P.nside + 1;
+                    if (jj + 1 < P.nside && kx < len && !used[kr] && !used[kd] && !used[kx]) {
+                        row[n++] = (unsigned char)k;  row[n++] = (unsigned char)kr;  row[n++] = (unsigned char)kd;  row[n++] = (unsigned char)kx;
+                        used[k] = used[kr] = used[kd] = used[kx] = true;
+                    }
+                }
+                for (int k = 0; k < len; k++) if (!used[k]) row[n++] = (unsigned char)k;
+            }
+            s0 = s1;
+        }
     }
     P.refpitch = c->refpitch;
     P.tau_color = p.tau_color;  P.tau_gradient = p.tau_gradient;  P.alpha = p.alpha;  P.gamma = p.gamma;
@@ -858,6 +887,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     }
     else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
+    else if (n == "quadperm") c->opt_quadperm = value != 0;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

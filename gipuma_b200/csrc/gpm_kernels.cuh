@@ -5,6 +5,13 @@
 
 namespace gpm {
 
+__host__ __device__ inline int tile_floats(const KParams& P) { return P.tile_w * P.tile_w * (P.color ? 4 : 1); }
+__host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (tile_floats(P) + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
+__device__ __forceinline__ unsigned char* block_perm(const KParams& P, float* smem_base)
+{
+    return reinterpret_cast<unsigned char*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4);
+}
+
 // Stage the (32+2*halo)^2 reference window of tile (bx, by) and the per-view camera table in shared memory.
 // Unlike the reference's loader (gipuma.cu:1510-1525, skipped by threads that left early — SURVEY.md §7),
 // every thread takes part, so the whole window is always defined.
@@ -29,6 +36,10 @@ __device__ __forceinline__ void stage_block(const KParams& P, const float* __res
     }
     const float* c = reinterpret_cast<const float*>(cams);
     for (int e = threadIdx.x; e < P.V * GPM_VIEWCAM_FLOATS; e += blockDim.x) sCam[e] = c[e];
+    // lane -> sample table of the sampling rounds (KParams::perm), word by word
+    unsigned* sp = reinterpret_cast<unsigned*>(block_perm(P, tile));
+    const unsigned* gp = reinterpret_cast<const unsigned*>(&P.perm[0][0]);
+    for (int e = threadIdx.x; e < GPM_MAX_ROUNDS * 8; e += blockDim.x) sp[e] = gp[e];
 }
 
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, const WarpStats& st, unsigned lane)
@@ -42,12 +53,10 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const War
     }
 }
 
-// shared memory: [tile tw*tw][cams V*21][pad to 16 B][nwarps * warp_scratch][1 int work counter]
-__host__ __device__ inline int tile_floats(const KParams& P) { return P.tile_w * P.tile_w * (P.color ? 4 : 1); }
-__host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (tile_floats(P) + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
+// shared memory: [tile tw*tw][cams V*21][pad to 16 B][nwarps * warp_scratch][4 ints: work counter][lane permutation table, GPM_MAX_ROUNDS x 32 bytes]
 __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
 {
-    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4;
+    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4 + GPM_MAX_ROUNDS * 8;
     return fl * sizeof(float);
 }
 
@@ -105,7 +114,7 @@ k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams,
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     WarpStats st = {0, 0, 0, 0, 0};
     for (int idx = warp; idx < GPM_TILE * GPM_TILE; idx += P.nwarps) {
         const int px = blockIdx.x * GPM_TILE + (idx & 31), py = blockIdx.y * GPM_TILE + (idx >> 5);
@@ -152,7 +161,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
     if (threadIdx.x == 0) *counter = P.nwarps;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H;
@@ -363,7 +372,7 @@ k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
     __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
