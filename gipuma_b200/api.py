@@ -89,14 +89,20 @@ def load_library():
     L.gpm_shard_num_stages.argtypes = [vp]
     L.gpm_shard_stage_floats.argtypes = [vp, C.c_int]
     L.gpm_shard_stage_floats.restype = C.c_longlong
-    L.gpm_shard_eval.argtypes = [vp, C.c_int, C.c_int, vp]
-    L.gpm_shard_accept.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+    L.gpm_shard_stage.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.gpm_shard_finish_init.argtypes = [vp, vp, C.c_int]
+    L.gpm_shard_unique_id.argtypes = [vp]
+    L.gpm_shard_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.gpm_shard_comm_attach.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.gpm_shard_run.argtypes = [vp, fp]
+    L.gpm_measure_fetch_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.gpm_stream.restype = vp
     for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_reference_color",
                  "gpm_set_view_color", "gpm_set_num_views",
                  "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
                  "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option",
-                 "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_eval", "gpm_shard_accept",
+                 "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_stage", "gpm_shard_finish_init", "gpm_shard_unique_id",
+                 "gpm_shard_comm_init", "gpm_shard_comm_attach", "gpm_shard_run", "gpm_measure_fetch_peak",
                  "gpm_prepare_cameras", "gpm_select_views", "gpm_write_dmb", "gpm_read_dmb", "gpm_write_result_dmb"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -276,17 +282,37 @@ class Context:
             self._check(int(n))
         return int(n)
 
-    def shard_eval(self, colour: int, stage: int, xchg):
-        self._check(self.lib.gpm_shard_eval(self.h, colour, stage, C.c_void_p(xchg.data_ptr())))
+    def shard_stage(self, colour: int, stage: int, gathered_prev, world: int, xchg):
+        """Accept of the previous stage (from `gathered_prev`, device tensor or None) + evaluation of `stage` into `xchg`."""
+        gp = C.c_void_p(gathered_prev.data_ptr()) if gathered_prev is not None else None
+        xp = C.c_void_p(xchg.data_ptr()) if xchg is not None else None
+        self._check(self.lib.gpm_shard_stage(self.h, colour, stage, gp, world, xp))
 
-    def shard_accept(self, colour: int, stage: int, gathered, world: int):
-        self._check(self.lib.gpm_shard_accept(self.h, colour, stage, C.c_void_p(gathered.data_ptr()), world))
+    def shard_finish_init(self, gathered, world: int):
+        self._check(self.lib.gpm_shard_finish_init(self.h, C.c_void_p(gathered.data_ptr()), world))
+
+    def shard_comm_init(self, unique_id: Optional[bytes], rank: int, world: int):
+        """ncclCommInitRank behind the C-ABI; `unique_id` = the 128 bytes of shard_unique_id() of the group's rank 0."""
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        self._check(self.lib.gpm_shard_comm_init(self.h, buf, rank, world))
+
+    def shard_run(self) -> float:
+        """runcuda() with sharded views (gpm_shard_run): returns the sweep time in ms."""
+        ms = C.c_float(0)
+        self._check(self.lib.gpm_shard_run(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def stats(self) -> dict:
         s = (C.c_ulonglong * 8)()
         self._check(self.lib.gpm_get_stats(self.h, s))
         return {"launches": s[0], "hypotheses": s[1], "skipped": s[2], "pruned": s[3],
-                "pairs": s[4], "pairs_full": s[5]}
+                "pairs": s[4], "pairs_full": s[5], "collectives": s[6]}
+
+    def measure_fetch_peak(self) -> float:
+        """Texture-unit ceiling on this GPU, in 1e9 filtered R32F fetches per second (gpm_measure_fetch_peak)."""
+        v = C.c_double(0)
+        self._check(self.lib.gpm_measure_fetch_peak(self.h, C.byref(v)))
+        return float(v.value)
 
     def reset_stats(self):
         self._check(self.lib.gpm_reset_stats(self.h))
@@ -294,6 +320,16 @@ class Context:
     @property
     def stream(self) -> int:
         return int(self.lib.gpm_stream(self.h) or 0)
+
+
+def shard_unique_id() -> bytes:
+    """128-byte NCCL unique id for gpm_shard_comm_init (call on the shard group's rank 0, broadcast to the others)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.gpm_shard_unique_id(buf)
+    if rc != 0:
+        raise GipumaError("gpm_shard_unique_id: %s" % lib.gpm_last_error().decode())
+    return buf.raw
 
 
 class LineState:

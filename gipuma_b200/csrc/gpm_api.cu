@@ -50,13 +50,25 @@ struct gpm_ctx {
     float* dispbuf = nullptr;        // view-shard mode: disp_now carried between the stages of one colour
     float4* candbuf = nullptr;       // view-shard mode: refinement candidate of the current step
     float* canddepth = nullptr;
+    unsigned char* sflags = nullptr; // view-shard mode: per-pixel flags of the current colour pass (GPM_SF_*)
+    float* xchg = nullptr;           // view-shard mode: this rank's lists of the current stage / all ranks' lists (gpm_shard_run)
+    float* gath = nullptr;
+    size_t xchg_floats = 0;
+    int gath_world = 0;
+    void* comm = nullptr;            // ncclComm_t of the shard group
+    bool comm_owned = false;
+    int shard_rank = 0, shard_world = 0;
+    unsigned long long collectives = 0;
     float4* seen = nullptr;          // [H*W*ncand] last plane offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
     int seen_slots = 8;
     float4* refseen = nullptr;       // [H*W]   plane from which the last all-rejected refinement started
     unsigned* memo_mask = nullptr;   // [H*W] validity bits of seen (0-19) and refseen (GPM_MEMO_REFINE)
     unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
-    int refpitch = 0;
+    int refpitch = 0, refrows = 0;   // padded reference image: refrows x refpitch texels
+    CUtensorMap tmap{};              // 2-D TMA descriptor of the padded reference image for the current box size / image type
+    int tmap_box = 0, tmap_color = -1;
+    int opt_tma = 1;
     float* staging = nullptr;        // W*H floats, upload scratch
     cudaArray_t srcArr = nullptr;
     cudaTextureObject_t srcTex = 0;
@@ -97,6 +109,37 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// 2-D TMA descriptor (cuTensorMapEncodeTiled, fetched through the runtime so that the library links only cudart) of the
+// padded reference image: box = one tile's window, tile_stride x tile_w texels (float4 images: 4 floats per texel).
+int ensure_tensor_map(gpm_ctx* c, const KParams& P)
+{
+    const int box = c->prm.box_hsize;
+    if (c->tmap_box == box && c->tmap_color == P.color) return GPM_OK;
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(GPM_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeTiled)fn;
+    }
+    const int comps = P.color ? 4 : 1;
+    void* base = P.color ? (void*)c->refpad4 : (void*)c->refpad;
+    const cuuint64_t gdim[2] = {(cuuint64_t)c->refpitch * comps, (cuuint64_t)c->refrows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)c->refpitch * comps * sizeof(float)};
+    const cuuint32_t bdim[2] = {(cuuint32_t)(P.tile_stride * comps), (cuuint32_t)P.tile_w};
+    const cuuint32_t estr[2] = {1, 1};
+    if (bdim[0] > 256 || bdim[1] > 256) return fail(GPM_E_ARG, "window too large for one TMA box");
+    const CUresult r = encode(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(GPM_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    c->tmap_box = box;  c->tmap_color = P.color;
+    return GPM_OK;
+}
+
 int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = false)
 {
     if (!c->have_params) return fail(GPM_E_STATE, "gpm_set_params has not been called");
@@ -114,6 +157,7 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     P.ns_pad = (P.ns + 3) & ~3;
     P.halo = (box + 1) / 2;                                 // gipuma.cu:1844-1847
     P.tile_w = GPM_TILE + 2 * P.halo;
+    P.tile_stride = (P.tile_w + 15) & ~15;                  // 48 or 64 texels: TMA box rows of 192 / 256 bytes (176- and 240-byte rows fault on B200)
     // rounds of 32 consecutive samples (one per lane); the remainder forms a last, shorter round.  A window with
     // fewer than 48 samples (b <= 11) is split into two equal rounds instead.
     {
@@ -161,6 +205,9 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     P.min_disp = p.min_disparity;  P.max_disp = p.max_disparity;
     P.n_best = p.n_best;  P.cost_comb = p.cost_comb;  P.good_factor = p.good_factor;
     P.prune = c->opt_prune;
+    // The lower bound counts a view as valid from its PARTIAL cost; a view whose final cost reaches MAXCOST (then excluded,
+    // gipuma.cu:771-774) would make the bound exceed the final value.  Unreachable while ns * max dissimilarity < MAXCOST.
+    if ((float)P.ns * ((1.0f - p.alpha) * p.tau_color + p.alpha * p.tau_gradient) >= GPM_MAXCOST) P.prune = 0;
     P.dedupe_self = c->opt_dedupe ? 1 : 0;
     // rounding variant of k_cost_eval: at initialisation the reference's binary is y-first for float, x-first for float4;
     // gpm_cost_eval defaults to the variant of the propagation kernels (x-first for float, y-first for float4)
@@ -205,6 +252,11 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     }
     if (block_smem_bytes(P) > (size_t)c->smem_optin)
         return fail(GPM_E_ARG, "configuration needs more shared memory per block than the device offers");
+    P.use_tma = c->opt_tma ? 1 : 0;
+    if (P.use_tma) {
+        int rc = ensure_tensor_map(c, P);
+        if (rc) return rc;
+    }
     return GPM_OK;
 }
 
@@ -226,7 +278,7 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
     grid.z = split;
     auto kern = P.ncand == 20 ? (P.color ? k_sweep<false, true, true> : k_sweep<false, false, true>)
                               : (P.color ? k_sweep<false, true, false> : (P.packed ? k_sweep<true, false, false> : k_sweep<false, false, false>));
-    kern<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
+    kern<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
                                                       c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -286,7 +338,9 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     c->view_8bit.assign(max_views, 0);
     c->h_cams.assign(max_views, ViewCam{});
     const size_t n = (size_t)width * height;
-    c->refpitch = (width + 2 * GPM_APRON + 31) & ~31;
+    // the staged window of the last tile row / column reaches roundup(size, 32) + halo + GPM_APRON (+ 3 texels of TMA row padding)
+    c->refpitch = (((width + 31) & ~31) + 2 * GPM_APRON + 4 + 31) & ~31;
+    c->refrows = ((height + 31) & ~31) + 2 * GPM_APRON;
     cudaError_t err = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (err == cudaSuccess && r != cudaSuccess) err = r; return r == cudaSuccess; };
     ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -300,7 +354,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned)));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
     ok(cudaMalloc(&c->d_flag, sizeof(int)));
-    ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * (height + 2 * GPM_APRON) * sizeof(float)));
+    ok(cudaMalloc(&c->refpad, (size_t)c->refpitch * c->refrows * sizeof(float)));
     ok(cudaMalloc(&c->d_cams, sizeof(ViewCam) * max_views));
     ok(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
     if (err == cudaSuccess) {
@@ -330,9 +384,9 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaFuncSetAttribute(k_cost_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
-        ok(cudaFuncSetAttribute(k_shard_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_stage<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_stage<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_stage<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
     }
     if (err != cudaSuccess) {
         std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
@@ -343,11 +397,14 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     return GPM_OK;
 }
 
+static void gpm_shard_comm_destroy_(gpm_ctx* c);
+
 extern "C" void gpm_destroy(gpm_ctx* c)
 {
     if (!c) return;
     DeviceGuard g(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && c->comm_owned) gpm_shard_comm_destroy_(c);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
     if (c->srcTex4) cudaDestroyTextureObject(c->srcTex4);
@@ -356,7 +413,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
     if (c->gradArr) cudaFreeArray(c->gradArr);
     cudaFree(c->gradLin);  cudaFree(c->d_flag);
-    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->seen);  cudaFree(c->refseen);  cudaFree(c->memo_mask);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->seen);  cudaFree(c->refseen);  cudaFree(c->memo_mask);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->sflags);  cudaFree(c->xchg);  cudaFree(c->gath);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -385,6 +442,11 @@ extern "C" int gpm_set_params(gpm_ctx* c, const gpm_params* p)
 extern "C" int gpm_set_num_views(gpm_ctx* c, int n)
 {
     if (!c || n < 1 || n > c->maxV) return fail(GPM_E_ARG, "gpm_set_num_views: out of range");
+    if (n != c->V) {                       // the cost function changes with the view count: stored costs / memo are stale
+        DeviceGuard g(c->device);
+        CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
+    }
     c->V = n;
     return GPM_OK;
 }
@@ -413,8 +475,8 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     if (rc) return rc;
     rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);
     if (rc) return rc;
-    dim3 b(32, 8), gr((c->W + 2 * GPM_APRON + 31) / 32, (c->H + 2 * GPM_APRON + 7) / 8);
-    k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch);
+    dim3 b(32, 8), gr((c->refpitch + 31) / 32, (c->refrows + 7) / 8);
+    k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch, c->refrows);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
     CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
@@ -495,7 +557,7 @@ static int ensure_color(gpm_ctx* c, int want)
         td.addressMode[0] = cudaAddressModeWrap;  td.addressMode[1] = cudaAddressModeWrap;  td.addressMode[2] = cudaAddressModeClamp;
         td.filterMode = cudaFilterModeLinear;  td.readMode = cudaReadModeElementType;  td.normalizedCoords = 0;
         CU(cudaCreateTextureObject(&c->srcTex4, &res, &td, NULL));
-        CU(cudaMalloc(&c->refpad4, (size_t)c->refpitch * (c->H + 2 * GPM_APRON) * sizeof(float4)));
+        CU(cudaMalloc(&c->refpad4, (size_t)c->refpitch * c->refrows * sizeof(float4)));
         CU(cudaMalloc(&c->staging4, (size_t)c->W * c->H * sizeof(float4)));
     }
     return GPM_OK;
@@ -523,8 +585,8 @@ extern "C" int gpm_set_reference_color(gpm_ctx* c, const float* rgba, size_t pit
     size_t pe = 0;
     rc = upload_image4(c, rgba, pitch_bytes, on_device, &d, &pe);
     if (rc) return rc;
-    dim3 b(32, 8), gr((c->W + 2 * GPM_APRON + 31) / 32, (c->H + 2 * GPM_APRON + 7) / 8);
-    k_pad_reference4<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->refpad4, c->refpitch);
+    dim3 b(32, 8), gr((c->refpitch + 31) / 32, (c->refrows + 7) / 8);
+    k_pad_reference4<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->refpad4, c->refpitch, c->refrows);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
     CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
@@ -609,7 +671,7 @@ static int do_init(gpm_ctx* c)
     c->launches++;
     CU(cudaGetLastError());
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes,
+    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes,
                                                                          c->cost, nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -707,12 +769,13 @@ extern "C" int gpm_cost_eval(gpm_ctx* c, const float* planes, float* out_cost, i
     float* d_out = nullptr;
     if (on_device) { d_pl = (float4*)planes;  d_out = out_cost; }
     else {
-        CU(cudaMalloc(&d_pl, n * sizeof(float4)));
-        CU(cudaMalloc(&d_out, n * sizeof(float)));
-        CU(cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+        cudaError_t e1 = cudaMalloc(&d_pl, n * sizeof(float4));
+        if (e1 == cudaSuccess) e1 = cudaMalloc(&d_out, n * sizeof(float));
+        if (e1 == cudaSuccess) e1 = cudaMemcpyAsync(d_pl, planes, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream);
+        if (e1 != cudaSuccess) { cudaFree(d_pl);  cudaFree(d_out);  return fail(GPM_E_CUDA, std::string("gpm_cost_eval: ") + cudaGetErrorString(e1)); }
     }
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
-    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, d_pl, d_out, nullptr);
+    (P.color ? k_cost_eval<false, true> : (P.packed ? k_cost_eval<true, false> : k_cost_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, d_pl, d_out, nullptr);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !on_device) e = cudaMemcpyAsync(out_cost, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
@@ -772,7 +835,9 @@ static int shard_common(gpm_ctx* c, int stage, KParams& P)
     if (c->prm.cost_comb != GPM_COMB_BEST_N) return fail(GPM_E_ARG, "view sharding supports cost_comb = best_n only");
     if (c->opt_neighbours != 8) return fail(GPM_E_ARG, "view sharding supports the 8-neighbour sweep only (option neighbours = 8)");
     if (c->prm.n_best < 1 || c->prm.n_best > 32) return fail(GPM_E_ARG, "view sharding needs 1 <= n_best <= 32");
-    if (stage < 0 || stage >= 2 + shard_refine_steps(c->prm)) return fail(GPM_E_ARG, "no such stage");
+    if (c->rng_mode != GPM_RNG_REFERENCE) return fail(GPM_E_ARG, "view sharding implements the reference's zero-state refinement stream only (GPM_RNG_REFERENCE)");
+    const int last = 1 + shard_refine_steps(c->prm);
+    if (stage < 0 || stage > last + 1) return fail(GPM_E_ARG, "no such stage");
     int rc = build_kparams(c, stage == 0, P);
     if (rc) return rc;
     rc = sync_cams(c);
@@ -782,42 +847,226 @@ static int shard_common(gpm_ctx* c, int stage, KParams& P)
         CU(cudaMalloc(&c->dispbuf, n * sizeof(float)));
         CU(cudaMalloc(&c->candbuf, n * sizeof(float4)));
         CU(cudaMalloc(&c->canddepth, n * sizeof(float)));
+        CU(cudaMalloc(&c->sflags, n));
+        CU(cudaMemsetAsync(c->sflags, 0, n, c->stream));
     }
     return GPM_OK;
 }
 
-extern "C" int gpm_shard_eval(gpm_ctx* c, int colour, int stage, float* xchg_dev)
+// enqueue one stage kernel (stage 0 .. last+1) on the context's stream
+static int shard_launch_stage(gpm_ctx* c, const KParams& P, int colour, int stage, const float* gathered_prev, int world, float* xchg)
 {
-    if (!c || !xchg_dev || colour < 0 || colour > 1) return fail(GPM_E_ARG, "gpm_shard_eval: bad arguments");
-    DeviceGuard g(c->device);
-    KParams P;
-    int rc = shard_common(c, stage, P);
-    if (rc) return rc;
+    const int last = 1 + shard_refine_steps(c->prm);
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
     int split = 1;                                        // at least ~8 waves of blocks, as in launch_colour
     while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
     grid.z = split;
-    (P.color ? k_shard_eval<false, true> : (P.packed ? k_shard_eval<true, false> : k_shard_eval<false, false>))<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost,
-                                                                          c->prov, c->dispbuf, c->candbuf, c->canddepth, c->seen, c->memo_mask, colour, stage, xchg_dev);
+    ShardState S{c->dispbuf, c->candbuf, c->canddepth, c->sflags};
+    auto kern = P.color ? k_shard_stage<false, true> : (P.packed ? k_shard_stage<true, false> : k_shard_stage<false, false>);
+    kern<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad,
+        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, c->seen, c->refseen, c->memo_mask, colour, stage, last,
+        gathered_prev, world, xchg, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
-    if (!c->opt_shard_async) CU(cudaStreamSynchronize(c->stream));       // the caller's collective may run on another stream
     return GPM_OK;
 }
 
-extern "C" int gpm_shard_accept(gpm_ctx* c, int colour, int stage, const float* gathered_dev, int world)
+extern "C" int gpm_shard_stage(gpm_ctx* c, int colour, int stage, const float* gathered_prev_dev, int world, float* xchg_dev)
 {
-    if (!c || !gathered_dev || colour < 0 || colour > 1 || world < 1 || world > 8) return fail(GPM_E_ARG, "gpm_shard_accept: bad arguments");
+    if (!c || colour < 0 || colour > 1 || world < 1 || world > 8) return fail(GPM_E_ARG, "gpm_shard_stage: bad arguments");
     DeviceGuard g(c->device);
     KParams P;
     int rc = shard_common(c, stage, P);
     if (rc) return rc;
+    const int last = 1 + shard_refine_steps(c->prm);
+    if (stage >= 2 && !gathered_prev_dev) return fail(GPM_E_ARG, "gpm_shard_stage: stages >= 2 need the gathered lists of the previous stage");
+    if (stage <= last && !xchg_dev) return fail(GPM_E_ARG, "gpm_shard_stage: no exchange buffer");
+    rc = shard_launch_stage(c, P, colour, stage, gathered_prev_dev, world, xchg_dev);
+    if (rc) return rc;
+    if (!c->opt_shard_async) CU(cudaStreamSynchronize(c->stream));       // the caller's collective may run on another stream
+    return GPM_OK;
+}
+
+extern "C" int gpm_shard_finish_init(gpm_ctx* c, const float* gathered_dev, int world)
+{
+    if (!c || !gathered_dev || world < 1 || world > 8) return fail(GPM_E_ARG, "gpm_shard_finish_init: bad arguments");
+    DeviceGuard g(c->device);
+    KParams P;
+    int rc = shard_common(c, 0, P);
+    if (rc) return rc;
     dim3 b(32, 8), gr(((P.W + 1) / 2 + 31) / 32, (P.H + 7) / 8);
-    k_shard_accept<<<gr, b, 0, c->stream>>>(P, c->planes, c->cost, c->prov, c->dispbuf, c->candbuf, c->canddepth, colour, stage,
-                                            gathered_dev, world);
+    k_shard_accept0<<<gr, b, 0, c->stream>>>(P, c->cost, c->prov, gathered_dev, world);
     c->launches++;
     CU(cudaGetLastError());
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     if (!c->opt_shard_async) CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+// ---- the exchange behind the C-ABI: NCCL, loaded at run time (a C++ host needs no torch) ---------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+};
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {getenv("GPM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n) continue;
+            api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.h) break;
+        }
+        if (api.h) {
+            api.GetUniqueId = (int (*)(NcclId*))dlsym(api.h, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.h, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(void*))dlsym(api.h, "ncclCommDestroy");
+            api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.h, "ncclAllGather");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.h, "ncclGetErrorString");
+            api.GetVersion = (int (*)(int*))dlsym(api.h, "ncclGetVersion");
+            if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather) { dlclose(api.h);  api.h = nullptr; }
+        }
+    }
+    return api.h ? &api : nullptr;
+}
+}  // namespace
+
+#define NC(call)                                                                                                        \
+    do {                                                                                                                \
+        int e_ = (call);                                                                                                \
+        if (e_ != 0) return fail(GPM_E_CUDA, std::string(#call) + ": NCCL error " + (nccl_api() && nccl_api()->GetErrorString ? nccl_api()->GetErrorString(e_) : "?")); \
+    } while (0)
+
+static void gpm_shard_comm_destroy_(gpm_ctx* c)
+{
+    if (c->comm && c->comm_owned && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    c->comm = nullptr;  c->comm_owned = false;
+}
+
+extern "C" int gpm_shard_unique_id(void* id128)
+{
+    if (!id128) return fail(GPM_E_ARG, "gpm_shard_unique_id: null argument");
+    NcclApi* n = nccl_api();
+    if (!n) return fail(GPM_E_STATE, "NCCL (libnccl.so.2) could not be loaded; set GPM_NCCL_LIB");
+    NC(n->GetUniqueId((NcclId*)id128));
+    return GPM_OK;
+}
+
+static int shard_alloc_exchange(gpm_ctx* c)
+{
+    long long mx = 0;
+    const int ns = gpm_shard_num_stages(c);
+    for (int st = 0; st < ns; st++) { const long long f = gpm_shard_stage_floats(c, st);  if (f > mx) mx = f; }
+    if (c->xchg && c->xchg_floats >= (size_t)mx && c->gath_world >= c->shard_world) return GPM_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(c->xchg);  cudaFree(c->gath);  c->xchg = c->gath = nullptr;
+    CU(cudaMalloc(&c->xchg, (size_t)mx * sizeof(float)));
+    CU(cudaMalloc(&c->gath, (size_t)mx * sizeof(float) * c->shard_world));
+    c->xchg_floats = (size_t)mx;  c->gath_world = c->shard_world;
+    return GPM_OK;
+}
+
+extern "C" int gpm_shard_comm_init(gpm_ctx* c, const void* id128, int rank, int world)
+{
+    if (!c || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(GPM_E_ARG, "gpm_shard_comm_init: bad arguments (1 <= world <= 8)");
+    DeviceGuard g(c->device);
+    if (c->comm && c->comm_owned) { nccl_api()->CommDestroy(c->comm); }
+    c->comm = nullptr;  c->comm_owned = false;
+    c->shard_rank = rank;  c->shard_world = world;
+    if (world > 1) {
+        if (!id128) return fail(GPM_E_ARG, "gpm_shard_comm_init: null unique id");
+        NcclApi* n = nccl_api();
+        if (!n) return fail(GPM_E_STATE, "NCCL (libnccl.so.2) could not be loaded; set GPM_NCCL_LIB");
+        NcclId id;  memcpy(&id, id128, sizeof(id));
+        NC(n->CommInitRank(&c->comm, world, id, rank));
+        c->comm_owned = true;
+    }
+    return GPM_OK;
+}
+
+extern "C" int gpm_shard_comm_attach(gpm_ctx* c, void* nccl_comm, int rank, int world)
+{
+    if (!c || world < 1 || world > 8 || rank < 0 || rank >= world || (world > 1 && !nccl_comm)) return fail(GPM_E_ARG, "gpm_shard_comm_attach: bad arguments");
+    if (world > 1 && !nccl_api()) return fail(GPM_E_STATE, "NCCL (libnccl.so.2) could not be loaded; set GPM_NCCL_LIB");
+    if (c->comm && c->comm_owned) nccl_api()->CommDestroy(c->comm);
+    c->comm = nccl_comm;  c->comm_owned = false;  c->shard_rank = rank;  c->shard_world = world;
+    return GPM_OK;
+}
+
+// all-gather of this rank's lists of one stage (rank-major result), on the context's stream
+static int shard_exchange(gpm_ctx* c, int stage)
+{
+    const size_t n = (size_t)gpm_shard_stage_floats(c, stage);
+    if (c->shard_world == 1) { CU(cudaMemcpyAsync(c->gath, c->xchg, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));  return GPM_OK; }
+    NC(nccl_api()->AllGather(c->xchg, c->gath, n, 7 /* ncclFloat32 */, c->comm, c->stream));
+    c->collectives++;
+    return GPM_OK;
+}
+
+// runcuda() with the source views sharded over the ranks of the attached communicator.  Every rank calls it with the same
+// parameters, reference image and seed and ITS views; all work — kernels and collectives — is enqueued on the context's
+// stream, one host synchronisation at the end.
+extern "C" int gpm_shard_run(gpm_ctx* c, float* sweep_ms)
+{
+    if (!c) return fail(GPM_E_ARG, "null context");
+    if (c->shard_world < 1) return fail(GPM_E_STATE, "gpm_shard_run: no communicator (gpm_shard_comm_init / gpm_shard_comm_attach)");
+    DeviceGuard g(c->device);
+    KParams P0, P;
+    int rc = shard_common(c, 0, P0);
+    if (rc) return rc;
+    rc = shard_common(c, 1, P);
+    if (rc) return rc;
+    rc = shard_alloc_exchange(c);
+    if (rc) return rc;
+    const int world = c->shard_world, last = 1 + shard_refine_steps(c->prm);
+    CU(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
+    c->launches = 0;  c->collectives = 0;
+    {
+        dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
+        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
+        rc = shard_launch_stage(c, P0, 0, 0, nullptr, world, c->xchg);
+        if (rc) return rc;
+        rc = shard_exchange(c, 0);
+        if (rc) return rc;
+        dim3 b2(32, 8), gr2(((P0.W + 1) / 2 + 31) / 32, (P0.H + 7) / 8);
+        k_shard_accept0<<<gr2, b2, 0, c->stream>>>(P0, c->cost, c->prov, c->gath, world);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(c->ev0, c->stream));
+    for (int it = 0; it < c->prm.iterations; it++)
+        for (int colour = 0; colour < 2; colour++) {
+            for (int stage = 1; stage <= last; stage++) {
+                rc = shard_launch_stage(c, P, colour, stage, c->gath, world, c->xchg);
+                if (rc) return rc;
+                rc = shard_exchange(c, stage);
+                if (rc) return rc;
+            }
+            rc = shard_launch_stage(c, P, colour, last + 1, c->gath, world, c->xchg);     // closing accept of the colour
+            if (rc) return rc;
+        }
+    rc = do_finalize(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (sweep_ms) *sweep_ms = ms;
+    CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
 
@@ -833,7 +1082,30 @@ extern "C" int gpm_init_planes(gpm_ctx* c)
     k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr);
     c->launches++;
     CU(cudaGetLastError());
+    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));      // every plane is new: costs and memo are stale
+    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+extern "C" int gpm_measure_fetch_peak(gpm_ctx* c, double* gfetch_per_s)
+{
+    if (!c || !gfetch_per_s) return fail(GPM_E_ARG, "gpm_measure_fetch_peak: null argument");
+    if (c->V < 1 || c->color < 0) return fail(GPM_E_STATE, "gpm_measure_fetch_peak: no source views");
+    DeviceGuard g(c->device);
+    float* sink = reinterpret_cast<float*>(c->d_stats + 7);
+    const int blocks = c->num_sms * 16, threads = 256, reps = 2048;
+    const cudaTextureObject_t tex = c->color == 1 ? c->srcTex4 : c->srcTex;      // colour: three R32F channel planes per view
+    const int layers = c->color == 1 ? 3 * c->V : c->V;
+    k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, c->W, c->H, layers, 64, sink);        // warm-up
+    CU(cudaEventRecord(c->ev0, c->stream));
+    k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, c->W, c->H, layers, reps, sink);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *gfetch_per_s = (double)blocks * threads * reps * 5.0 / (ms * 1e6);
     return GPM_OK;
 }
 
@@ -844,6 +1116,7 @@ extern "C" int gpm_get_stats(gpm_ctx* c, unsigned long long stats[8])
     CU(cudaMemcpyAsync(stats, c->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     stats[ST_LAUNCH] = c->launches;
+    stats[6] = c->collectives;
     return GPM_OK;
 }
 
@@ -888,6 +1161,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "packed") { c->opt_packed = value;  if (value) for (auto& f : c->view_8bit) f = 0; }   // set BEFORE uploading views;            // 0 off (default), 1 auto, 2 force — EXPERIMENTAL, see DESIGN.md §5
     else if (n == "memo") c->opt_memo = value != 0;
     else if (n == "quadperm") c->opt_quadperm = value != 0;
+    else if (n == "tma") c->opt_tma = value != 0;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

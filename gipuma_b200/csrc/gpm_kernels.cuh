@@ -1,38 +1,79 @@
 // gpm_kernels.cuh — __global__ kernels of the PatchMatch hot path (sm_100a).  See gpm_device.cuh.
 #pragma once
 #include "gpm_device.cuh"
+#include <cuda.h>                 // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <curand_kernel.h>
 
 namespace gpm {
 
-__host__ __device__ inline int tile_floats(const KParams& P) { return P.tile_w * P.tile_w * (P.color ? 4 : 1); }
+__host__ __device__ inline int tile_floats(const KParams& P) { return P.tile_stride * P.tile_w * (P.color ? 4 : 1); }
 __host__ __device__ inline int fixed_smem_floats(const KParams& P) { return (tile_floats(P) + P.V * GPM_VIEWCAM_FLOATS + 3) & ~3; }
+__device__ __forceinline__ unsigned long long* block_mbar(const KParams& P, float* smem_base)
+{
+    return reinterpret_cast<unsigned long long*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 2);
+}
 __device__ __forceinline__ unsigned char* block_perm(const KParams& P, float* smem_base)
 {
     return reinterpret_cast<unsigned char*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4);
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives -------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (int spin = 0; !done; spin++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();          // a lost TMA transaction must fail loudly, not hang the GPU
+    }
+}
+
 // Stage the (32+2*halo)^2 reference window of tile (bx, by) and the per-view camera table in shared memory.
 // Unlike the reference's loader (gipuma.cu:1510-1525, skipped by threads that left early — SURVEY.md §7),
-// every thread takes part, so the whole window is always defined.
-__device__ __forceinline__ void stage_block(const KParams& P, const float* __restrict__ refpad,
+// the whole window is always defined.  With P.use_tma one elected thread issues a single 2-D TMA box copy
+// (cp.async.bulk.tensor) from the replicate-padded reference image and the block waits on its mbarrier while the other
+// threads copy the camera and lane tables; otherwise the window is a cooperative copy.  `phase` = parity of the barrier's
+// current phase (0 for the first / only tile of a block).
+__device__ __forceinline__ void stage_block(const KParams& P, const CUtensorMap* tmap, const float* __restrict__ refpad,
                                             const ViewCam* __restrict__ cams, float* tile, float* sCam,
-                                            int tile_x0, int tile_y0)
+                                            int tile_x0, int tile_y0, unsigned phase = 0u)
 {
-    const int tw = P.tile_w;
-    if (P.color) {                                  // float4 texels: refpitch counts float4 elements
+    const int tw = P.tile_w, ts = P.tile_stride;
+    unsigned long long* bar = block_mbar(P, tile);
+    if (P.use_tma) {
+        if (threadIdx.x == 0) {
+            if (phase == 0u) mbar_init(bar, 1);
+            mbar_arrive_expect_tx(bar, (unsigned)(tile_floats(P) * sizeof(float)));
+            tma_load_2d(tile, tmap, (tile_x0 + GPM_APRON) * (P.color ? 4 : 1), tile_y0 + GPM_APRON, bar);
+        }
+    } else if (P.color) {                           // float4 texels: refpitch counts float4 elements
         const float4* src4 = reinterpret_cast<const float4*>(refpad) + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
         float4* tile4 = reinterpret_cast<float4*>(tile);
         for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
             const int J = e / tw, I = e - J * tw;
-            tile4[e] = src4[(size_t)J * P.refpitch + I];
+            tile4[J * ts + I] = src4[(size_t)J * P.refpitch + I];
         }
     } else {
-    const float* src = refpad + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
-    for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
-        const int J = e / tw, I = e - J * tw;
-        tile[e] = src[(size_t)J * P.refpitch + I];
-    }
+        const float* src = refpad + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
+        for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
+            const int J = e / tw, I = e - J * tw;
+            tile[J * ts + I] = src[(size_t)J * P.refpitch + I];
+        }
     }
     const float* c = reinterpret_cast<const float*>(cams);
     for (int e = threadIdx.x; e < P.V * GPM_VIEWCAM_FLOATS; e += blockDim.x) sCam[e] = c[e];
@@ -40,6 +81,8 @@ __device__ __forceinline__ void stage_block(const KParams& P, const float* __res
     unsigned* sp = reinterpret_cast<unsigned*>(block_perm(P, tile));
     const unsigned* gp = reinterpret_cast<const unsigned*>(&P.perm[0][0]);
     for (int e = threadIdx.x; e < GPM_MAX_ROUNDS * 8; e += blockDim.x) sp[e] = gp[e];
+    __syncthreads();                                // tables visible; mbarrier initialised before anyone waits on it
+    if (P.use_tma) mbar_wait(bar, phase & 1u);
 }
 
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, const WarpStats& st, unsigned lane)
@@ -53,7 +96,7 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const War
     }
 }
 
-// shared memory: [tile tw*tw][cams V*21][pad to 16 B][nwarps * warp_scratch][4 ints: work counter][lane permutation table, GPM_MAX_ROUNDS x 32 bytes]
+// shared memory: [tile tile_stride*tile_w][cams V*21][pad to 16 B][nwarps * warp_scratch][4 ints: work counter, -, mbarrier (8 B)][lane permutation table, GPM_MAX_ROUNDS x 32 bytes]
 __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
 {
     size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4 + GPM_MAX_ROUNDS * 8;
@@ -102,18 +145,17 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
 #endif
 template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
-k_cost_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+k_cost_eval(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
             cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, float* __restrict__ cost,
             unsigned long long* __restrict__ stats)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* tile = smem;
     float* sCam = tile + tile_floats(P);
     float* scratch = smem + fixed_smem_floats(P);
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
-    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
-    __syncthreads();
+    stage_block(P, &tmap, refpad, cams, tile, sCam, tile_x0, tile_y0);
     const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     WarpStats st = {0, 0, 0, 0, 0};
     for (int idx = warp; idx < GPM_TILE * GPM_TILE; idx += P.nwarps) {
@@ -145,13 +187,13 @@ __device__ const signed char kFusedGy1[20] = { 0,  0,  0, 1, 3, 5,  0,  0,  0, 0
 
 template <bool PACKED, bool COLOR, bool FUSED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
-k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
         unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, float4* __restrict__ seen,
         float4* __restrict__ refseen, unsigned* __restrict__ memo_mask, int colour, int phase_mask,
         unsigned long long* __restrict__ stats)
 {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* tile = smem;
     float* sCam = tile + tile_floats(P);
     float* scratch = smem + fixed_smem_floats(P);
@@ -159,8 +201,7 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
     if (threadIdx.x == 0) *counter = P.nwarps;
-    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
-    __syncthreads();
+    stage_block(P, &tmap, refpad, cams, tile, sCam, tile_x0, tile_y0);
     const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
@@ -344,140 +385,32 @@ k_sweep(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, con
 }
 
 // ============================================================================================================
-// Source-view sharding across GPUs (BASELINE config 4).  Every rank holds the full plane/cost state
-// and a SUBSET of the source views.  Per-view costs are independent (gipuma.cu:742-778); only the combination needs
-// all views.  For COMB_BEST_N the n_best smallest costs over all views are the n_best smallest of the union of every
-// rank's n_best smallest, so each rank exports, per pixel and hypothesis slot, its ascending local top-n_best
-// (k_shard_eval), the lists are all-gathered over NCCL, and every rank merges them, sums in ascending order — the
-// reference's order (gipuma.cu:779-797) — and applies the accept logic redundantly (k_shard_accept).  All ranks
-// therefore keep bit-identical state, identical to a single-GPU run over all views.
-//   stage 0        initial cost of the stored planes        (1 slot,  radius box/2)
+// Source-view sharding across GPUs (BASELINE configs 4 / 5, north_star's strong-scaling axis).
+// Every rank holds the full plane/cost state and a SUBSET of the source views.  Per-view costs are independent
+// (gipuma.cu:742-778); only the combination needs all views.  For COMB_BEST_N the n_best smallest costs over all views
+// are the n_best smallest of the union of every rank's n_best smallest, so each rank exports, per pixel and hypothesis
+// slot, its ascending local top-n_best; the lists of all ranks are exchanged (NCCL all-gather, or peer stores over NVLink
+// in the fused kernel below) and every rank merges them, sums in ascending order — the reference's order
+// (gipuma.cu:779-797) — and applies the accept logic redundantly.  All ranks therefore keep bit-identical state,
+// identical to a single-GPU run over all views.
+//   stage 0        initial cost of the stored planes        (1 slot,  radius box/2, both colours)
 //   stage 1        close + far propagation candidates       (8 slots)
 //   stage 2 + s    refinement step s                         (1 slot; sequential: step s+1 depends on step s' accept)
+// The accept of stage s is FUSED into the evaluation of stage s+1 (shard_stage_pixel): a colour costs 1 + S evaluation
+// passes plus one closing accept instead of 2 (1 + S) launches.  The exact shortcuts of k_sweep that depend only on the
+// shared state are kept — direction memo, history, duplicates (incl. the current plane), refinement memo — so every rank
+// skips the same work and the skipped slots simply carry +inf lists.
 // Exchange index of pixel (x, y): y * ceil(W/2) + x/2 (pixels of one colour have distinct x/2 within a row).
 // ============================================================================================================
-template <bool PACKED, bool COLOR>
-__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
-k_shard_eval(const __grid_constant__ KParams P, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
-             cudaTextureObject_t src, cudaTextureObject_t grad, const float4* __restrict__ planes, const float* __restrict__ cost,
-             const unsigned char* __restrict__ prov, float* __restrict__ dispbuf, float4* __restrict__ candbuf,
-             float* __restrict__ canddepth, float4* __restrict__ seen, unsigned* __restrict__ memo_mask,
-             int colour, int stage, float* __restrict__ xchg)
-{
-    extern __shared__ __align__(16) float smem[];
-    float* tile = smem;
-    float* sCam = tile + tile_floats(P);
-    float* scratch = smem + fixed_smem_floats(P);
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
-    stage_block(P, refpad, cams, tile, sCam, tile_x0, tile_y0);
-    __syncthreads();
-    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
-    const RefCam& cam = P.ref;
-    WarpStats st = {0, 0, 0, 0, 0};
-    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
-    const int slots = (stage == 1) ? 8 : 1;
-    const float inf = __int_as_float(0x7f800000);
-    // stage 0 visits every pixel (both colours, like gipuma_init_cu2); the others one colour
-    const int npix = (stage == 0) ? GPM_TILE * GPM_TILE : GPM_TILE * GPM_TILE / 2;
-    // gridDim.z slices of the tile's pixel list, as in k_sweep: small images would otherwise leave most SMs idle in the
-    // last wave (640x480 = 300 tiles on 148 SMs)
-    const int per_slice = (npix + (int)gridDim.z - 1) / (int)gridDim.z;
-    const int idx_end = min(npix, ((int)blockIdx.z + 1) * per_slice);
-    for (int idx = (int)blockIdx.z * per_slice + (int)warp; idx < idx_end; idx += P.nwarps) {
-        int px, py;
-        if (stage == 0) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
-        else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }
-        if (px >= W || py >= H) continue;
-        const size_t center = (size_t)py * W + px;
-        // stage 0 exchanges both colours: two half-resolution planes back to back
-        float* out = xchg + (((stage == 0 ? (size_t)((px + py) & 1) * H * Wh : 0) + (size_t)py * Wh + (px >> 1)) * slots) * nb;
-        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
-        const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
-        const float4 norm_now = planes[center];
-        float c0, c1;
-        if (stage == 0) {
-            eval_plane<(COLOR ? 1 : 0), PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);   // init variant
-            local_topn(P, c0, c1, lane, out);
-        } else if (stage == 1) {
-            const int prov_now = prov[center];
-            if (lane == 0) dispbuf[center] = plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
-            float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool mine_ok = false;
-            if (lane < 8) {
-                const int dist = lane < 4 ? 1 : 5, dir = lane & 3;
-                int qx = px, qy = py;
-                bool ok;
-                if (dir == 0)      { ok = py > dist - 1;  qy = py - dist; }
-                else if (dir == 1) { ok = py < H - dist;  qy = py + dist; }
-                else if (dir == 2) { ok = px > dist - 1;  qx = px - dist; }
-                else               { ok = px < W - dist;  qx = px + dist; }
-                mine_ok = ok;
-                if (mine_ok) mine = planes[(size_t)qy * W + qx];
-            }
-            // direction memo of rejected work, as in k_sweep (identical on every rank: it only depends on the shared state)
-            const unsigned mmask = P.memo ? memo_mask[center] : 0u;
-            bool memo_hit = false;
-            if (P.memo && mine_ok && ((mmask >> lane) & 1)) {
-                const float4 old = seen[center * 8 + lane];
-                memo_hit = __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
-                           __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
-            }
-            const unsigned memo_bits = __ballot_sync(GPM_FULL, memo_hit);
-            const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
-            if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
-            if (P.memo && lane == 0 && (mmask | (cand_mask & 0xffu)) != mmask) memo_mask[center] = mmask | (cand_mask & 0xffu);
-            for (int k = 0; k < 8; k++) {
-                float4 nbp;
-                nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
-                nbp.z = __shfl_sync(GPM_FULL, mine.z, k);  nbp.w = __shfl_sync(GPM_FULL, mine.w, k);
-                bool skip = !((cand_mask >> k) & 1) || ((memo_bits >> k) & 1);
-                if (!skip) {
-                    const float d = plane_depth(cam, nbp.x, nbp.y, nbp.z, nbp.w, fpx, fpy);
-                    const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
-                    // self-dedupe is only neutral against the cost at kernel entry if no earlier slot is accepted; the
-                    // accept kernel cannot know, so only the candidate-vs-candidate rule is used here
-                    const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k &&                                            __float_as_uint(nbp.x) == __float_as_uint(mine.x) && __float_as_uint(nbp.y) == __float_as_uint(mine.y) &&
-                                           __float_as_uint(nbp.z) == __float_as_uint(mine.z) && __float_as_uint(nbp.w) == __float_as_uint(mine.w);
-                    skip = !in_range || __any_sync(GPM_FULL, same_mine);
-                    (void)prov_now;
-                }
-                if (skip) { if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-                eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
-                local_topn(P, c0, c1, lane, out + k * nb);
-            }
-        } else {
-            // refinement step s = stage - 2: getRndDispAndUnitVector_cu with the zero-state stream advanced by 4*s draws
-            const int sidx = stage - 2;
-            Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};
-            float deltaZ = fmul(P.max_disp, 0.5f), deltaN = 1.0f;
-            for (int i = 0; i < sidx; i++) { for (int j = 0; j < 4; j++) xorwow_next(r);  deltaZ = fmul(deltaZ, 0.1f);  deltaN = fmul(deltaN, 0.25f); }
-            const float disp_now = dispbuf[center];
-            float vx, vy, vz;
-            view_vector(cam, fpx, fpy, vx, vy, vz);
-            const float fb = fmul(cam.baseline, cam.f);
-            const float rdisp = frcp(disp_now);
-            const float hi = fmin_(ffma(rdisp, -fb, P.max_disp), deltaZ);
-            const float lo = fmin_(ffma(rdisp, fb, P.min_disp), deltaZ);
-            const float dz = ffma(xorwow_uniform(r), fadd(lo, hi), -lo);
-            float dnew = ffma(rdisp, fb, dz);
-            dnew = fmin_(P.max_disp, fmax_(P.min_disp, dnew));
-            const float depth_new = fmul(frcp(dnew), fb);
-            const float twoN = fadd(deltaN, deltaN);
-            const float ax = fadd(norm_now.x, ffma(xorwow_uniform(r), twoN, -deltaN));
-            const float ay = fadd(norm_now.y, ffma(twoN, xorwow_uniform(r), -deltaN));
-            const float az = fadd(norm_now.z, ffma(twoN, xorwow_uniform(r), -deltaN));
-            const float rs = frsq(ffma(az, az, ffma(ax, ax, fmul(ay, ay))));
-            float4 cand;
-            cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
-            if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
-            cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
-            if (lane == 0) { candbuf[center] = cand;  canddepth[center] = depth_new; }
-            eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
-            local_topn(P, c0, c1, lane, out);
-        }
-    }
-}
+#define GPM_SF_SKIP_REFINE 1u     // sflags: the refinement of this colour pass is known to reject every step (memo)
+#define GPM_SF_ACCEPTED    2u     // sflags: some refinement step of this colour pass was accepted
+
+struct ShardState {
+    float* dispbuf;               // disp_now carried between the stages of one colour
+    float4* candbuf;              // refinement candidate of the step being exchanged
+    float* canddepth;
+    unsigned char* sflags;
+};
 
 // merged cost of one slot: the n_best smallest over all ranks' lists, summed ascending, / count  (gipuma.cu:779-803)
 __device__ __forceinline__ float shard_merge(const float* __restrict__ g, size_t rank_stride, int world, int nb)
@@ -489,7 +422,7 @@ __device__ __forceinline__ float shard_merge(const float* __restrict__ g, size_t
         float best = __int_as_float(0x7f800000);
         int br = -1;
         for (int r = 0; r < world; r++) {
-            if (pos[r] < nb) { const float v = g[r * rank_stride + pos[r]]; if (v < best) { best = v;  br = r; } }
+            if (pos[r] < nb) { const float v = __ldcg(g + r * rank_stride + pos[r]); if (v < best) { best = v;  br = r; } }
         }
         if (br < 0 || !(best < GPM_MAXCOST)) break;        // only views with c < MAXCOST count (numValidViews)
         pos[br]++;
@@ -502,50 +435,237 @@ __device__ __forceinline__ float shard_merge(const float* __restrict__ g, size_t
     return cost;
 }
 
-__global__ void k_shard_accept(const __grid_constant__ KParams P, float4* __restrict__ planes, float* __restrict__ cost,
-                               unsigned char* __restrict__ prov, float* __restrict__ dispbuf,
-                               const float4* __restrict__ candbuf, const float* __restrict__ canddepth,
-                               int colour, int stage, const float* __restrict__ gathered, int world)
+__device__ __forceinline__ bool same_bits(const float4& a, const float4& b)
+{
+    return __float_as_uint(a.x) == __float_as_uint(b.x) && __float_as_uint(a.y) == __float_as_uint(b.y) &&
+           __float_as_uint(a.z) == __float_as_uint(b.z) && __float_as_uint(a.w) == __float_as_uint(b.w);
+}
+
+// refinement candidate of step `sidx` from (norm_now, disp_now) — getRndDispAndUnitVector_cu, gipuma.cu:890-927, with the
+// reference's zero-state stream (pin P2) advanced by 4 draws per earlier step
+__device__ __forceinline__ float4 shard_refine_candidate(const KParams& P, const float4& norm_now, float disp_now, float fpx, float fpy,
+                                                         int sidx, float& depth_new)
+{
+    const RefCam& cam = P.ref;
+    Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};
+    float deltaZ = fmul(P.max_disp, 0.5f), deltaN = 1.0f;
+    for (int i = 0; i < sidx; i++) { for (int j = 0; j < 4; j++) xorwow_next(r);  deltaZ = fmul(deltaZ, 0.1f);  deltaN = fmul(deltaN, 0.25f); }
+    float vx, vy, vz;
+    view_vector(cam, fpx, fpy, vx, vy, vz);
+    const float fb = fmul(cam.baseline, cam.f);
+    const float rdisp = frcp(disp_now);
+    const float hi = fmin_(ffma(rdisp, -fb, P.max_disp), deltaZ);
+    const float lo = fmin_(ffma(rdisp, fb, P.min_disp), deltaZ);
+    const float dz = ffma(xorwow_uniform(r), fadd(lo, hi), -lo);
+    float dnew = ffma(rdisp, fb, dz);
+    dnew = fmin_(P.max_disp, fmax_(P.min_disp, dnew));
+    depth_new = fmul(frcp(dnew), fb);
+    const float twoN = fadd(deltaN, deltaN);
+    const float ax = fadd(norm_now.x, ffma(xorwow_uniform(r), twoN, -deltaN));
+    const float ay = fadd(norm_now.y, ffma(twoN, xorwow_uniform(r), -deltaN));
+    const float az = fadd(norm_now.z, ffma(twoN, xorwow_uniform(r), -deltaN));
+    const float rs = frsq(ffma(az, az, ffma(ax, ax, fmul(ay, ay))));
+    float4 cand;
+    cand.x = fmul(ax, rs);  cand.y = fmul(ay, rs);  cand.z = fmul(az, rs);
+    if (dot3(cand.x, cand.y, cand.z, vx, vy, vz) > 0.0f) { cand.x = -cand.x;  cand.y = -cand.y;  cand.z = -cand.z; }
+    cand.w = plane_d(cam, cand.x, cand.y, cand.z, fpx, fpy, depth_new);
+    return cand;
+}
+
+// Accept of stage `stage` at pixel (px, py) from the exchanged lists (one warp; every lane returns the same state).
+// stage 1: the 8 propagation slots in the reference's order (gipuma.cu:1571-1582, 1450-1462; accept rule :867-871);
+// stage >= 2: one refinement step (:986-990).
+__device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float4* __restrict__ planes, const ShardState& S,
+                                                   int px, int py, int stage, const float* __restrict__ gathered, int world,
+                                                   float4& norm_now, float& cost_now, float& disp_now, int& prov_now, unsigned& sf,
+                                                   unsigned lane)
+{
+    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
+    const size_t center = (size_t)py * W + px;
+    const int slots = (stage == 1) ? 8 : 1;
+    const size_t per_rank = (size_t)H * Wh * slots * nb;
+    const float* g = gathered + ((size_t)py * Wh + (px >> 1)) * slots * nb;
+    const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
+    if (stage == 1) {
+        float mine = GPM_MAXCOST;
+        if (lane < 8) mine = shard_merge(g + lane * nb, per_rank, world, nb);
+        for (int k = 0; k < 8; k++) {
+            const float c = __shfl_sync(GPM_FULL, mine, k);
+            if (c < cost_now) {
+                const int dist = k < 4 ? 1 : 5, dir = k & 3;
+                const int qx = px + (dir == 2 ? -dist : dir == 3 ? dist : 0), qy = py + (dir == 0 ? -dist : dir == 1 ? dist : 0);
+                norm_now = planes[(size_t)qy * W + qx];                 // other colour: not written during this colour's stages
+                disp_now = plane_depth(P.ref, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
+                cost_now = c;
+                prov_now = P.color ? 0 : 1;
+            }
+        }
+    } else if (!(sf & GPM_SF_SKIP_REFINE)) {
+        const float c = shard_merge(g, per_rank, world, nb);
+        if (c < cost_now) {
+            cost_now = c;  norm_now = S.candbuf[center];  disp_now = S.canddepth[center];  prov_now = 0;
+            sf |= GPM_SF_ACCEPTED;
+        }
+    }
+}
+
+// One stage of one pixel: [accept of stage-1's exchange] + evaluation of `stage` on this rank's views -> local top-n lists.
+template <bool PACKED, bool COLOR>
+__device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float* __restrict__ sCam, const float* __restrict__ tile,
+                                                  const WarpScratch& ws, cudaTextureObject_t src, cudaTextureObject_t grad,
+                                                  float4* __restrict__ planes, float* __restrict__ cost, unsigned char* __restrict__ prov,
+                                                  const ShardState& S, float4* __restrict__ seen, float4* __restrict__ refseen,
+                                                  unsigned* __restrict__ memo_mask, int px, int py, int tile_x0, int tile_y0,
+                                                  int stage, int last_stage, const float* __restrict__ gathered_prev, int world,
+                                                  float* __restrict__ xchg, unsigned lane, WarpStats& st)
+{
+    const RefCam& cam = P.ref;
+    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
+    const size_t center = (size_t)py * W + px;
+    const float inf = __int_as_float(0x7f800000);
+    const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
+    float c0, c1;
+    float4 norm_now = planes[center];
+    if (stage == 0) {                                       // initial costs (gipuma.cu:1040-1049), both colours: two half-resolution planes
+        float* out = xchg + ((size_t)((px + py) & 1) * H * Wh + (size_t)py * Wh + (px >> 1)) * nb;
+        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        eval_plane<(COLOR ? 1 : 0), PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
+        local_topn(P, c0, c1, lane, out);
+        return;
+    }
+    float cost_now = cost[center];
+    int prov_now = prov[center];
+    unsigned sf = stage >= 2 ? (unsigned)S.sflags[center] : 0u;
+    float disp_now = stage >= 2 ? S.dispbuf[center] : plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
+    unsigned mmask = P.memo ? memo_mask[center] : 0u;
+    unsigned new_mask = mmask;
+    if (stage >= 2) {
+        shard_accept_pixel(P, planes, S, px, py, stage - 1, gathered_prev, world, norm_now, cost_now, disp_now, prov_now, sf, lane);
+        if (stage == 2) {
+            // refinement memo (see k_sweep): the S candidates are a pure function of (pixel, plane at refinement start)
+            sf = 0u;
+            if (P.memo && P.rng_mode == 0) {
+                if ((mmask & GPM_MEMO_REFINE) && same_bits(refseen[center], norm_now)) sf = GPM_SF_SKIP_REFINE;
+                else { if (lane == 0) refseen[center] = norm_now;  new_mask &= ~GPM_MEMO_REFINE; }
+            }
+        }
+    }
+    float* out = xchg + ((size_t)py * Wh + (px >> 1)) * (stage == 1 ? 8 : 1) * nb;
+    if (stage > last_stage) {                               // closing pass of a colour: only the accept of the last refinement step
+        if (P.memo && P.rng_mode == 0 && !(sf & (GPM_SF_SKIP_REFINE | GPM_SF_ACCEPTED))) new_mask |= GPM_MEMO_REFINE;
+    } else if (stage == 1) {
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool mine_ok = false;
+        if (lane < 8) {
+            const int dist = lane < 4 ? 1 : 5, dir = lane & 3;
+            int qx = px, qy = py;
+            bool ok;
+            if (dir == 0)      { ok = py > dist - 1;  qy = py - dist; }
+            else if (dir == 1) { ok = py < H - dist;  qy = py + dist; }
+            else if (dir == 2) { ok = px > dist - 1;  qx = px - dist; }
+            else               { ok = px < W - dist;  qx = px + dist; }
+            mine_ok = ok;
+            if (mine_ok) mine = planes[(size_t)qy * W + qx];
+        }
+        const bool old_ok = P.memo && lane < 8 && ((mmask >> lane) & 1);
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (old_ok) old = seen[center * 8 + lane];
+        const bool memo_hit = old_ok && mine_ok && same_bits(old, mine);
+        const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
+        const int site = COLOR ? 0 : 1;
+        bool window_ready = false;
+        for (int k = 0; k < 8; k++) {
+            float4 nbp;
+            nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
+            nbp.z = __shfl_sync(GPM_FULL, mine.z, k);  nbp.w = __shfl_sync(GPM_FULL, mine.w, k);
+            bool skip = !((cand_mask >> k) & 1);
+            if (!skip) skip = __any_sync(GPM_FULL, old_ok && same_bits(nbp, old));          // offered before, from any direction
+            if (!skip) {
+                const float d = plane_depth(cam, nbp.x, nbp.y, nbp.z, nbp.w, fpx, fpy);
+                const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
+                // a plane equal to the current one (cost of the same rounding variant) or to an earlier slot can never pass
+                // `cost < cost_now`: cost_now only decreases while the slots are accepted in order
+                const bool same_now = P.dedupe_self && prov_now == site && same_bits(nbp, norm_now);
+                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && same_bits(nbp, mine);
+                skip = !in_range || same_now || __any_sync(GPM_FULL, same_mine);
+            }
+            if (skip) { st.skip++;  if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
+            if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+            eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
+            local_topn(P, c0, c1, lane, out + k * nb);
+        }
+        if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
+        new_mask |= (cand_mask & 0xffu);
+    } else {
+        if (sf & GPM_SF_SKIP_REFINE) {
+            st.skip++;
+            if ((int)lane < nb) out[lane] = inf;
+        } else {
+            float depth_new;
+            const float4 cand = shard_refine_candidate(P, norm_now, disp_now, fpx, fpy, stage - 2, depth_new);
+            if (lane == 0) { S.candbuf[center] = cand;  S.canddepth[center] = depth_new; }
+            setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+            eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
+            local_topn(P, c0, c1, lane, out);
+        }
+    }
+    if (lane == 0) {
+        if (stage >= 2) { planes[center] = norm_now;  cost[center] = cost_now;  prov[center] = (unsigned char)prov_now; }
+        if (stage >= 1) { S.dispbuf[center] = disp_now;  S.sflags[center] = (unsigned char)sf; }
+        if (P.memo && new_mask != mmask) memo_mask[center] = new_mask;
+    }
+}
+
+// One exchange stage over the whole image (NCCL flow: the all-gather runs between two launches of this kernel).
+// stage 0: both colours; 1 .. last_stage: one colour; last_stage + 1: closing accept of the colour.
+template <bool PACKED, bool COLOR>
+__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
+k_shard_stage(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
+              cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
+              unsigned char* __restrict__ prov, ShardState S, float4* __restrict__ seen, float4* __restrict__ refseen,
+              unsigned* __restrict__ memo_mask, int colour, int stage, int last_stage, const float* __restrict__ gathered_prev,
+              int world, float* __restrict__ xchg, unsigned long long* __restrict__ stats)
+{
+    extern __shared__ __align__(128) float smem[];
+    float* tile = smem;
+    float* sCam = tile + tile_floats(P);
+    float* scratch = smem + fixed_smem_floats(P);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
+    if (stage <= last_stage) stage_block(P, &tmap, refpad, cams, tile, sCam, tile_x0, tile_y0);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
+    WarpStats st = {0, 0, 0, 0, 0};
+    // stage 0 visits every pixel (both colours, like gipuma_init_cu2); the others one colour
+    const int npix = (stage == 0) ? GPM_TILE * GPM_TILE : GPM_TILE * GPM_TILE / 2;
+    // gridDim.z slices of the tile's pixel list, as in k_sweep
+    const int per_slice = (npix + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int idx_end = min(npix, ((int)blockIdx.z + 1) * per_slice);
+    for (int idx = (int)blockIdx.z * per_slice + (int)warp; idx < idx_end; idx += P.nwarps) {
+        int px, py;
+        if (stage == 0) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
+        else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }
+        if (px >= P.W || py >= P.H) continue;
+        shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, seen, refseen, memo_mask, px, py,
+                                         tile_x0, tile_y0, stage, last_stage, gathered_prev, world, xchg, lane, st);
+    }
+    flush_stats(stats, st, lane);
+}
+
+// closing accept of stage 0: merged initial costs for both colours (thread per half-row position)
+__global__ void k_shard_accept0(const __grid_constant__ KParams P, float* __restrict__ cost, unsigned char* __restrict__ prov,
+                                const float* __restrict__ gathered, int world)
 {
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
     const int hx = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (hx >= Wh || py >= H) return;
-    const int ncol = (stage == 0) ? 2 : 1;
-    for (int cc = 0; cc < ncol; cc++) {
-        const int col = (stage == 0) ? cc : colour;
+    const size_t per_rank = (size_t)2 * H * Wh * nb;
+    for (int col = 0; col < 2; col++) {
         const int px = 2 * hx + ((py + col) & 1);                      // the pixel of this colour with x/2 == hx in row py
         if (px >= W) continue;
         const size_t center = (size_t)py * W + px;
-        const int slots = (stage == 1) ? 8 : 1;
-        const size_t per_rank = (size_t)ncol * H * Wh * slots * nb;
-        const float* g = gathered + (((stage == 0 ? (size_t)col * H * Wh : 0) + (size_t)py * Wh + hx) * slots) * nb;
-        if (stage == 0) {
-            cost[center] = shard_merge(g, per_rank, world, nb);
-            prov[center] = P.color ? 3 : 0;          // initialisation variant
-        } else if (stage == 1) {
-            float4 norm_now = planes[center];
-            float cost_now = cost[center];
-            float disp_now = dispbuf[center];
-            int prov_now = prov[center];
-            const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
-            for (int k = 0; k < 8; k++) {
-                const float c = shard_merge(g + k * nb, per_rank, world, nb);
-                if (c < cost_now) {
-                    const int dist = k < 4 ? 1 : 5, dir = k & 3;
-                    const int qx = px + (dir == 2 ? -dist : dir == 3 ? dist : 0), qy = py + (dir == 0 ? -dist : dir == 1 ? dist : 0);
-                    norm_now = planes[(size_t)qy * W + qx];                 // other colour: not written by this launch
-                    disp_now = plane_depth(P.ref, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
-                    cost_now = c;
-                    prov_now = P.color ? 0 : 1;
-                }
-            }
-            planes[center] = norm_now;  cost[center] = cost_now;  dispbuf[center] = disp_now;  prov[center] = (unsigned char)prov_now;
-        } else {
-            const float c = shard_merge(g, per_rank, world, nb);
-            if (c < cost[center]) {
-                cost[center] = c;  planes[center] = candbuf[center];  dispbuf[center] = canddepth[center];  prov[center] = 0;
-            }
-        }
+        const float* g = gathered + ((size_t)col * H * Wh + (size_t)py * Wh + hx) * nb;
+        cost[center] = shard_merge(g, per_rank, world, nb);
+        prov[center] = P.color ? 3 : 0;          // initialisation variant
     }
 }
 
@@ -563,6 +683,30 @@ __global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict
     o.z = ffma(n.z, R[8], ffma(n.x, R[6], fmul(n.y, R[7])));
     o.w = (cost[center] != GPM_MAXCOST) ? plane_depth(P.ref, n.x, n.y, n.z, n.w, __int2float_rn(x), __int2float_rn(y)) : 0.0f;
     planes[center] = o;
+}
+
+// Ceiling of the unit that bounds this path, measured in process: filtered R32F fetches per second of the texture unit for
+// dense footprints (32 lanes = 8 x 4 adjacent texels, the best case of tools/texbench.cu) on the context's own layered
+// texture.  bench.py divides the fetch rate it achieves by this number (roofline.binding_unit).
+__global__ void k_fetch_peak(cudaTextureObject_t src, int W, int H, int V, int reps, float* __restrict__ sink)
+{
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const float dx = (float)(lane & 7), dy = (float)(lane >> 3);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    unsigned h = (unsigned)warp * 2654435761u + 12345u;
+    for (int r = 0; r < reps; r++) {
+        h = h * 1664525u + 1013904223u;
+        const float x = 8.0f + (float)((h >> 8) % (unsigned)(W - 32)) + 0.37f + dx;
+        const float y = 8.0f + (float)((h >> 4) % (unsigned)(H - 24)) + 0.61f + dy;
+        const int v = (int)((h >> 28) % (unsigned)V);
+        a0 += tex2DLayered<float>(src, x, y, v);
+        a1 += tex2DLayered<float>(src, x + 1.0f, y, v);
+        a2 += tex2DLayered<float>(src, x - 1.0f, y, v);
+        a3 += tex2DLayered<float>(src, x, y + 1.0f, v);
+        a4 += tex2DLayered<float>(src, x, y - 1.0f, v);
+    }
+    const float a = a0 + a1 + a2 + a3 + a4;
+    if (a == 12345.678f) sink[0] = a;
 }
 
 // Colour source views are sampled from three R32F planes (layer 3v + channel) instead of one RGBA32F layer.
@@ -590,20 +734,22 @@ __global__ void k_make_gradients(const float* __restrict__ img, size_t pitch_flo
     if (!(v >= 0.0f && v <= 255.0f && v == rintf(v))) *all_8bit = 0;
 }
 
-__global__ void k_pad_reference4(const float4* __restrict__ img, size_t pitch_elems, int W, int H, float4* __restrict__ out, int out_pitch)
+__global__ void k_pad_reference4(const float4* __restrict__ img, size_t pitch_elems, int W, int H, float4* __restrict__ out, int out_pitch, int out_rows)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W + 2 * GPM_APRON || y >= H + 2 * GPM_APRON) return;
+    if (x >= out_pitch || y >= out_rows) return;
     const int sx = min(max(x - GPM_APRON, 0), W - 1), sy = min(max(y - GPM_APRON, 0), H - 1);
     out[(size_t)y * out_pitch + x] = img[(size_t)sy * pitch_elems + sx];
 }
 
-// replicate-pad the reference image by GPM_APRON on every side (== the texture's clamp addressing, main.cpp:644-645)
+// replicate-pad the reference image by GPM_APRON on the left / top and out to the end of the allocation on the right / bottom
+// (== the texture's clamp addressing, main.cpp:644-645): the window of the last tile row / column reaches
+// roundup(size, 32) + halo + GPM_APRON, past size + 2 * GPM_APRON whenever size % 32 is small
 __global__ void k_pad_reference(const float* __restrict__ img, size_t pitch_floats, int W, int H,
-                                float* __restrict__ out, int out_pitch)
+                                float* __restrict__ out, int out_pitch, int out_rows)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W + 2 * GPM_APRON || y >= H + 2 * GPM_APRON) return;
+    if (x >= out_pitch || y >= out_rows) return;
     const int sx = min(max(x - GPM_APRON, 0), W - 1), sy = min(max(y - GPM_APRON, 0), H - 1);
     out[(size_t)y * out_pitch + x] = img[(size_t)sy * pitch_floats + sx];
 }

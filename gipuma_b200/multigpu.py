@@ -11,8 +11,8 @@ Two axes shard; the reference itself is single-GPU (main.cpp:65
    independent; only their combination needs all views (gipuma.cu:742-806).  `north_star` words this as "allreduce
    of best cost/plane", which is NOT the reference's rule (best-n over ALL views, summed in ascending order); the
    exact formulation used here: per stage, every rank exports per pixel and hypothesis slot its ascending n_best
-   smallest per-view costs (gpm_shard_eval), the lists are all-gathered (`dist.all_gather_into_tensor`, NCCL over
-   NVLink), and every rank merges, combines and applies the accept logic redundantly (gpm_shard_accept).  State
+   smallest per-view costs, the lists are all-gathered (ncclAllGather over NVLink, issued by gpm_shard_run behind the
+   C-ABI), and every rank merges, combines and applies the accept logic redundantly (fused into the next stage).  State
    stays bit-identical on all ranks and identical to a single-GPU run.  Collectives per iteration:
    2 colours x (1 propagation + S refinement steps) = 8 on DTU parameters; payload per rank and colour:
    H*ceil(W/2)*8*n_best*4 B for propagation (7.4 MB at 640x480, n_best 3), 1/8 of that per refinement step.
@@ -146,63 +146,53 @@ def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank
 # ----------------------------------------------------------------------------------------------------------------
 
 class ViewShardRunner:
-    """One reference view, source views sharded over the ranks of `group` (default: the world group)."""
+    """One reference view, source views sharded over `world` ranks.  All device work — stage kernels and the NCCL
+    all-gathers — runs behind the C-ABI (gpm_shard_run); torch.distributed is used once, to hand the 128-byte NCCL
+    unique id of the group's rank 0 to the other ranks."""
 
-    def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None):
-        import torch
+    def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None, options=None):
         from . import api
-        self.torch, self.scene, self.rank, self.world, self.group = torch, scene, rank, world, group
+        self.scene, self.rank, self.world, self.group = scene, rank, world, group
         self.local = partition_views(scene.n_views, world)[rank]
         if not self.local:
             raise ValueError("more ranks than source views")
         self.ctx = api.Context(scene.cols, scene.rows, len(self.local), device=device)
         ctx = self.ctx
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
         ctx.set_params(scene.params)
-        ctx.set_reference(np.ascontiguousarray(scene.images[0]), scene.cameras[0])
-        for v, pos in enumerate(self.local):
-            idx = scene.subset[pos]
-            ctx.set_view(v, np.ascontiguousarray(scene.images[idx]), scene.cameras[idx])
-        ctx.set_num_views(len(self.local))
+        self.upload(scene)
         ctx.set_rng(seed)
-        # every stage is enqueued on the context's own stream — kernels and the NCCL all-gather alike — so that the
-        # 2 x (1 + S) x iterations stages need no host synchronisation in between
-        ctx.set_option("shard_async", 1)
-        self.stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", device))
-        self.dev = torch.device("cuda", device)
-        self.n_stages = ctx.shard_num_stages()
-        self.xchg = {}
-        for st in range(self.n_stages):
-            n = ctx.shard_stage_floats(st)
-            if n not in self.xchg:
-                self.xchg[n] = (torch.empty(n, dtype=torch.float32, device=self.dev),
-                                torch.empty(n * world, dtype=torch.float32, device=self.dev))
-        self.stage_floats = [ctx.shard_stage_floats(st) for st in range(self.n_stages)]
+        uid = None
+        if world > 1:
+            import torch.distributed as dist
+            box = [api.shard_unique_id() if rank == 0 else None]
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=group)
+            uid = box[0]
+        ctx.shard_comm_init(uid, rank, world)
         self.collectives = 0
 
-    def _stage(self, colour: int, stage: int):
-        import torch.distributed as dist
-        loc, gat = self.xchg[self.stage_floats[stage]]
-        self.ctx.shard_eval(colour, stage, loc)
-        if self.world > 1:
-            dist.all_gather_into_tensor(gat, loc, group=self.group)     # ordered after shard_eval: same (current) stream
-            self.collectives += 1
-        else:
-            gat.copy_(loc)
-        self.ctx.shard_accept(colour, stage, gat, self.world)
+    def upload(self, scene, images=None):
+        """(Re)upload the reference image and this rank's views; `images` may be a list of pinned host tensors."""
+        imgs = scene.images if images is None else images
+        get = (lambda i: np.ascontiguousarray(imgs[i])) if isinstance(imgs, np.ndarray) else (lambda i: imgs[i])
+        self.ctx.set_reference(get(0), scene.cameras[0])
+        for v, pos in enumerate(self.local):
+            idx = scene.subset[pos]
+            self.ctx.set_view(v, get(idx), scene.cameras[idx])
+        self.ctx.set_num_views(len(self.local))
+
+    def run_timed(self) -> float:
+        """The sharded runcuda(); returns the sweep time in ms (reference's own span, max over ranks is the caller's job)."""
+        ms = self.ctx.shard_run()
+        self.collectives = self.ctx.stats()["collectives"]
+        return ms
 
     def run(self):
         """runcuda() with sharded views: returns (norm4, cost) like Context.get_state after gpm_run."""
-        ctx = self.ctx
-        with self.torch.cuda.stream(self.stream):
-            ctx.init_planes()                               # identical on all ranks (same seed)
-            self._stage(0, 0)                               # initial costs over all views
-            for _ in range(self.scene.params.iterations):
-                for colour in (0, 1):
-                    for stage in range(1, self.n_stages):
-                        self._stage(colour, stage)
-            ctx.finalize()
-        self.stream.synchronize()
-        return ctx.get_state()
+        self.run_timed()
+        return self.ctx.get_state()
 
     def close(self):
         self.ctx.close()

@@ -236,9 +236,12 @@ class HeightField:
     """Surface Z = f(X, Y) in the re-based frame (reference camera = K[I|0]) with a procedural
     texture T(X, Y).  `unit` is the world length of one reference pixel at depth z0."""
 
-    def __init__(self, z0: float, unit: float, seed: int = 1234, relief: float = 0.035, tilt=(0.10, -0.06)):
+    def __init__(self, z0: float, unit: float, seed: int = 1234, relief: float = 0.035, tilt=(0.10, -0.06), hard: bool = False):
         rng = np.random.default_rng(seed)
         self.z0, self.unit = float(z0), float(unit)
+        # "hard" variant (bench.py --scene hard): raised blocks with vertical walls (depth discontinuities -> occlusions
+        # between views), a texture-less band, and per-view sensor noise added by render_view
+        self.hard = bool(hard)
         self.tilt = tilt
         self.relief = relief * z0
         self.bump_wl = np.array([260.0, 410.0, 690.0]) * unit        # long waves: gentle slopes
@@ -255,6 +258,11 @@ class HeightField:
         z = self.z0 + self.tilt[0] * X + self.tilt[1] * Y
         for wl, a, ph in zip(self.bump_wl, self.bump_dir, self.bump_ph):
             z = z + (self.relief / 3.0) * np.sin(2 * np.pi * (X * np.cos(a) + Y * np.sin(a)) / wl + ph)
+        if self.hard:
+            # blocks standing 6 % of z0 proud of the surface on a 520-pixel lattice, 170 pixels wide
+            u = np.mod(X / (520.0 * self.unit) + 0.31, 1.0)
+            w = np.mod(Y / (520.0 * self.unit) + 0.17, 1.0)
+            z = z - 0.06 * self.z0 * ((u < 0.33) & (w < 0.33))
         return z
 
     def texture(self, X, Y):
@@ -274,12 +282,16 @@ class HeightField:
         a10 = L[(iw + 1) & 255, iu & 255]
         a11 = L[(iw + 1) & 255, (iu + 1) & 255]
         v += 30.0 * ((a00 * (1 - fu) + a01 * fu) * (1 - fw) + (a10 * (1 - fu) + a11 * fu) * fw)
+        if self.hard:
+            # texture-less horizontal band: 140 reference pixels tall, constant grey
+            band = np.abs(Y - 180.0 * self.unit) < 70.0 * self.unit
+            v = np.where(band, 131.0, v)
         return v
 
 
-def render_view(cam: Camera, rows: int, cols: int, hf: HeightField, iters: int = 10, band: int = 256):
+def render_view(cam: Camera, rows: int, cols: int, hf: HeightField, iters: int = 10, band: int = 256, noise_seed: Optional[int] = None):
     """Ray-cast the height field for every pixel of `cam`; returns (image float32 with integer values
-    in [0,255], depth along the camera's z axis)."""
+    in [0,255], depth along the camera's z axis).  `noise_seed`: add integer sensor noise in [-6, 6] (hard scenes)."""
     img = np.empty((rows, cols), dtype=np.float32)
     dep = np.empty((rows, cols), dtype=np.float32)
     Minv = cam.M_inv.astype(np.float64)
@@ -306,33 +318,55 @@ def render_view(cam: Camera, rows: int, cols: int, hf: HeightField, iters: int =
         Z = C[2] + lam * d[..., 2]
         img[y0:y1] = np.clip(np.rint(hf.texture(X, Y)), 0, 255).astype(np.float32)
         dep[y0:y1] = (R[2, 0] * X + R[2, 1] * Y + R[2, 2] * Z + t[2]).astype(np.float32)
+    if noise_seed is not None:
+        noise = np.random.default_rng(noise_seed).integers(-6, 7, size=img.shape)
+        img = np.clip(img + noise, 0, 255).astype(np.float32)
     return img, dep
+
+
+def _render_job(job):
+    cam, rows, cols, hf_args, noise_seed = job
+    return render_view(cam, rows, cols, HeightField(**hf_args), noise_seed=noise_seed)
 
 
 def render_scene(name: str, Ps: Sequence[np.ndarray], rows: int, cols: int, params: AlgorithmParameters,
                  cam_scale: float = 1.0, n_views: Optional[int] = None, z0: Optional[float] = None,
-                 seed: int = 1234, only_selected: bool = True) -> Scene:
+                 seed: int = 1234, only_selected: bool = True, hard: bool = False, workers: int = 0,
+                 render_positions: Optional[Sequence[int]] = None) -> Scene:
     """Prepare cameras, select views, render the reference and the selected source views, and
-    derive min/max_disparity from the depth range as main.cpp:898-906 does."""
+    derive min/max_disparity from the depth range as main.cpp:898-906 does.
+    `render_positions`: positions in the view subset to render (others stay zero) — a view-shard rank only needs the
+    reference image and its own views; `workers` > 1 renders the views in a fork pool (same bits)."""
     cams = prepare_cameras(Ps, cam_scale)
     subset = select_views(cams, cols, rows, params, n_views)
     keep = [0] + subset if only_selected else list(range(len(cams)))
     cams = [cams[i] for i in keep]
     subset = list(range(1, len(keep))) if only_selected else subset
     z0 = 0.5 * (params.depthMin + params.depthMax) if z0 is None else z0
-    hf = HeightField(z0=z0, unit=z0 / cams[0].fx, seed=seed)
-    images = np.empty((len(cams), rows, cols), dtype=np.float32)
+    hf_args = dict(z0=z0, unit=z0 / cams[0].fx, seed=seed, hard=hard)
+    images = np.zeros((len(cams), rows, cols), dtype=np.float32)
+    wanted = list(range(len(cams)))
+    if render_positions is not None and only_selected:
+        wanted = [0] + [1 + p for p in sorted(set(render_positions))]      # cams = [reference] + subset in order
+    jobs = [(cams[i], rows, cols, hf_args, (seed * 1000003 + 7919 * i) if hard else None) for i in wanted]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            results = pool.map(_render_job, jobs, chunksize=1)
+    else:
+        results = [_render_job(j) for j in jobs]
     gt = None
-    for i, c in enumerate(cams):
-        images[i], d = render_view(c, rows, cols, hf)
+    for i, (img, d) in zip(wanted, results):
+        images[i] = img
         if i == 0:
             gt = d
     f = np.float32(cams[0].f)
     b = np.float32(cams[0].baseline)
     params.min_disparity = float(f * b / np.float32(params.depthMax))     # main.cpp:905
     params.max_disparity = float(f * b / np.float32(params.depthMin))     # main.cpp:906
-    return Scene(name=name, rows=rows, cols=cols, images=images, cameras=cams, subset=subset, params=params,
-                 gt_depth=gt, meta={"z0": z0, "seed": seed, "cam_scale": cam_scale})
+    return Scene(name=name + ("_hard" if hard else ""), rows=rows, cols=cols, images=images, cameras=cams, subset=subset, params=params,
+                 gt_depth=gt, meta={"z0": z0, "seed": seed, "cam_scale": cam_scale, "hard": hard,
+                                    "rendered": wanted})
 
 
 def colorize(scene: Scene) -> Scene:
@@ -363,10 +397,13 @@ def _dtu_Ps() -> List[np.ndarray]:
 
 
 def make_config(k: int, rows: Optional[int] = None, cols: Optional[int] = None,
-                n_views: Optional[int] = None, iterations: Optional[int] = None, seed: int = 1234) -> Scene:
-    """The five BASELINE.json configurations.  `rows`/`cols`/`n_views`/
-    `iterations` override the configuration (used by tests to shrink a case; K is scaled with the
-    image so the geometry stays the same)."""
+                n_views: Optional[int] = None, iterations: Optional[int] = None, seed: int = 1234,
+                hard: bool = False, workers: int = 0, render_positions: Optional[Sequence[int]] = None) -> Scene:
+    """The five BASELINE.json configurations and, as k = 6, north_star's strong-scaling workload
+    (1600x1200, 60 source views, dtu_fast parameters).  `rows`/`cols`/`n_views`/`iterations` override the configuration
+    (used by tests to shrink a case; K is scaled with the image so the geometry stays the same); `hard` adds occluding
+    blocks, a texture-less band and sensor noise; `workers` / `render_positions` see render_scene."""
+    kw = dict(hard=hard, workers=workers, render_positions=render_positions)
     if k == 1:      # 320x240, 2 source views, 3 iterations, blocksize 15 — plumbing / parity
         W, H, V, it, b, nb = 320, 240, 2, 3, 15, 2
     elif k == 2:    # dtu_fast: blocksize 15, n_best 3, depth 300-800, angles 10-30 (scripts/dtu_fast.sh:10-21)
@@ -377,8 +414,10 @@ def make_config(k: int, rows: Optional[int] = None, cols: Optional[int] = None,
         W, H, V, it, b, nb = 640, 480, 47, 8, 11, 3
     elif k == 5:    # synthetic 3200x2400, 64 views
         W, H, V, it, b, nb = 3200, 2400, 64, 8, 15, 3
+    elif k == 6:    # north_star: "1600x1200 ... 60 source views", DTU shape, dtu_fast parameters (view-shard workload)
+        W, H, V, it, b, nb = 1600, 1200, 60, 8, 15, 3
     else:
-        raise ValueError("config must be 1..5")
+        raise ValueError("config must be 1..6")
     cols_ = W if cols is None else cols
     rows_ = H if rows is None else rows
     V = V if n_views is None else n_views
@@ -389,17 +428,17 @@ def make_config(k: int, rows: Optional[int] = None, cols: Optional[int] = None,
         K = np.array([[1520.4, 0, 302.32], [0, 1525.9, 246.87], [0, 0, 1.0]])
         scale = 640.0 / cols_
         Ps = synthetic_rig(V, K, distance=0.55, min_deg=5.0, max_deg=45.0, seed=seed)
-        return render_scene("cfg4_temple_ring", Ps, rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed)
+        return render_scene("cfg4_temple_ring", Ps, rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed, **kw)
     prm.depthMin, prm.depthMax, prm.min_angle, prm.max_angle = 300.0, 800.0, 10.0, 30.0
     if k == 5:
         K0, _, _ = decompose_projection(load_dtu_projections()[DTU_REF_POSITION])
         K0 = K0 / K0[2, 2]
         scale = 1600.0 / cols_          # 0.5 at 3200x2400: K x 2 (scaleK divides by the factor)
         Ps = synthetic_rig(V, K0, distance=550.0, min_deg=10.0, max_deg=30.0, seed=seed)
-        return render_scene("cfg5_synth_64v", Ps, rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed)
+        return render_scene("cfg5_synth_64v", Ps, rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed, **kw)
     scale = 1600.0 / cols_
-    name = {1: "cfg1_plumbing", 2: "cfg2_dtu_fast", 3: "cfg3_dtu_accurate"}[k]
-    return render_scene(name, _dtu_Ps(), rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed)
+    name = {1: "cfg1_plumbing", 2: "cfg2_dtu_fast", 3: "cfg3_dtu_accurate", 6: "dtu60_view_shard"}[k]
+    return render_scene(name, _dtu_Ps(), rows_, cols_, prm, cam_scale=scale, n_views=V, seed=seed, **kw)
 
 
 def params_as_dict(p: AlgorithmParameters) -> dict:

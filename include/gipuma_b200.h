@@ -122,25 +122,47 @@ int gpm_cost_eval(gpm_ctx* ctx, const float* planes, float* out_cost, int on_dev
 int gpm_run(gpm_ctx* ctx, float* sweep_ms);
 
 /* ---- source-view sharding across GPUs (cost_comb = best_n only) --------------------------------
- * Each rank creates a context holding ALL of the state but only ITS subset of the source views (gpm_set_view /
- * gpm_set_num_views with the local views).  Per stage, gpm_shard_eval writes this rank's ascending n_best smallest
- * per-view costs per pixel and hypothesis slot into `xchg_dev` (gpm_shard_stage_floats(stage) floats, device memory);
- * the caller all-gathers the buffers of all ranks (rank-major) and hands the result to gpm_shard_accept, which merges,
- * combines in the reference's order (gipuma.cu:779-803) and applies the accept logic.  Stages per colour:
- * 1 (8 propagation candidates), then 2 .. gpm_shard_num_stages()-1 (refinement steps, sequential).  Stage 0 computes
- * the initial costs after gpm_init_planes (both colours at once; `colour` ignored).  Results are bit-identical to a
- * single-GPU run over all views. */
+ * The reference is single-GPU (main.cpp:658-692); what is preserved is pmCostMultiview_cu's combination over ALL views
+ * (gipuma.cu:742-806).  Each rank creates a context holding ALL of the state but only ITS subset of the source views
+ * (gpm_set_view / gpm_set_num_views with the local views; same parameters, reference image and seed everywhere).
+ *
+ * High level — the whole runcuda() flow, exchange included, behind the C-ABI (a C++ host needs nothing else):
+ *   gpm_shard_unique_id(id)           rank 0: 128-byte NCCL unique id; distribute it to the other ranks by any means
+ *   gpm_shard_comm_init(ctx, id, r, n) every rank: ncclCommInitRank on the context's device (n = 1: no communicator)
+ *   gpm_shard_comm_attach(ctx, comm, r, n)   alternative: use an existing ncclComm_t of the shard group
+ *   gpm_shard_run(ctx, &ms)           init planes, initial costs, params.iterations sweeps, final kernel; per exchange
+ *                                     stage one ncclAllGather of the local top-n_best lists on the context's stream; no
+ *                                     host synchronisation in between.  Output bit-identical to gpm_run over all views.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2", override with GPM_NCCL_LIB); the library itself links only cudart.
+ *
+ * Low level (tests, custom transports): per stage, gpm_shard_stage applies the accept of the PREVIOUS stage from
+ * `gathered_prev_dev` (rank-major concatenation of every rank's lists; ignored for stages 0 and 1) and writes this
+ * rank's ascending n_best smallest per-view costs per pixel and hypothesis slot of THIS stage into `xchg_dev`
+ * (gpm_shard_stage_floats(stage) floats, device memory).  Stages per colour: 1 (8 propagation candidates), then
+ * 2 .. gpm_shard_num_stages()-1 (refinement steps, sequential), then gpm_shard_num_stages() (closing accept only, no
+ * output).  Stage 0 evaluates the initial costs after gpm_init_planes (both colours at once; `colour` ignored) and is
+ * closed by gpm_shard_finish_init. */
 int gpm_init_planes(gpm_ctx* ctx);
 int gpm_shard_num_stages(gpm_ctx* ctx);
 long long gpm_shard_stage_floats(gpm_ctx* ctx, int stage);
-int gpm_shard_eval(gpm_ctx* ctx, int colour, int stage, float* xchg_dev);
-int gpm_shard_accept(gpm_ctx* ctx, int colour, int stage, const float* gathered_dev, int world);
+int gpm_shard_stage(gpm_ctx* ctx, int colour, int stage, const float* gathered_prev_dev, int world, float* xchg_dev);
+int gpm_shard_finish_init(gpm_ctx* ctx, const float* gathered_dev, int world);
+int gpm_shard_unique_id(void* id128);
+int gpm_shard_comm_init(gpm_ctx* ctx, const void* id128, int rank, int world);
+int gpm_shard_comm_attach(gpm_ctx* ctx, void* nccl_comm, int rank, int world);
+int gpm_shard_run(gpm_ctx* ctx, float* sweep_ms);
 
 /* Counters of the last gpm_sweep/gpm_run: [0] kernels launched, [1] hypotheses offered,
  * [2] hypotheses skipped as exact duplicates / out of depth range, [3] hypotheses cut short by the
- * exact lower bound, [4] (view,sample) evaluations done, [5] (view,sample) evaluations a full run would do. */
+ * exact lower bound, [4] (view,sample) evaluations done, [5] (view,sample) evaluations a full run would do,
+ * [6] collectives issued by gpm_shard_run. */
 int gpm_get_stats(gpm_ctx* ctx, unsigned long long stats[8]);
 int gpm_reset_stats(gpm_ctx* ctx);
+
+/* Measured ceiling of the unit that bounds this path: filtered R32F fetches per second (in 1e9) of the texture unit for
+ * dense footprints on this context's own source-view texture (a ~30 ms microbenchmark; needs the views set).
+ * bench.py's roofline.binding_unit divides the achieved fetch rate by it. */
+int gpm_measure_fetch_peak(gpm_ctx* ctx, double* gfetch_per_s);
 
 /* Tuning / diagnostics; results are bit-identical for every setting.
  * "prune" (1): exact lower-bound early-out; "dedupe" (1): skip bit-identical candidate planes;
@@ -149,8 +171,9 @@ int gpm_reset_stats(gpm_ctx* ctx);
  * known to reject (exact); "cost_variant" (-1 = auto): which of the reference binary's rounding variants gpm_cost_eval
  * reproduces: bit 0 = x-term first (float: 1 in the propagation kernels, 0 at init / refinement; float4: 0 in
  * all six sweep kernels), bit 1 = float4 gradient folding (float4 initialisation = 3); auto = the propagation kernels' form;
- * "shard_async" (0): 1 makes gpm_shard_eval / gpm_shard_accept return after enqueueing on gpm_stream() — run the collective
- * on that stream (or order it with events) instead of paying two host synchronisations per stage;
+ * "shard_async" (0): 1 makes gpm_shard_stage / gpm_shard_finish_init return after enqueueing on gpm_stream() — run the
+ * collective on that stream (or order it with events) instead of paying a host synchronisation per stage;
+ * "quadperm" (1): deal the samples of a round to the lanes as 2x2 blocks per hardware quad (texture-unit locality);
  * "neighbours" (8): 20 selects the reference's fused sweep — the kernels it launches when built without SMALLKERNEL
  * (gipuma.cu:1122-1351, 1913-1940): 12 axial + 8 knight-move neighbours, then refinement, one launch per colour; bit-exact
  * like the default (view sharding stays 8-neighbour only).

@@ -1,6 +1,7 @@
 """Source-view sharding (multi-GPU mode) on one GPU: the ranks are simulated by separate contexts holding disjoint
 view subsets; the all-gather is a torch.cat.  The merged flow must reproduce the single-context run bit for bit.
-(The NCCL plumbing itself is exercised by tools/run_shard_nccl.py under torchrun on >= 2 GPUs and by the gloo tests.)"""
+(The NCCL exchange behind gpm_shard_run is exercised by test_gpu_view_shard_nccl.py when >= 2 GPUs are visible and by
+tools/run_shard_nccl.py under torchrun; the host-side list merging by the gloo tests.)"""
 import numpy as np
 import pytest
 
@@ -26,25 +27,29 @@ def _sharded_run(sc, world, seed=0xC0FFEE):
         ctxs.append(ctx)
     n_stages = ctxs[0].shard_num_stages()
 
-    def stage(colour, st):
-        n = ctxs[0].shard_stage_floats(st)
+    def stage(colour, st, prev):
+        """One exchange stage on every simulated rank: accept of the previous stage (fused) + evaluation; returns the
+        rank-major concatenation of the lists, i.e. what an all-gather hands to every rank."""
+        n = ctxs[0].shard_stage_floats(st) if st < n_stages else 0
         locs = []
         for ctx in ctxs:
-            buf = torch.empty(n, dtype=torch.float32, device="cuda")
-            ctx.shard_eval(colour, st, buf)
+            buf = torch.empty(n, dtype=torch.float32, device="cuda") if n else None
+            ctx.shard_stage(colour, st, prev, world, buf)
             locs.append(buf)
-        gathered = torch.cat(locs)                       # rank-major, what all_gather_into_tensor produces
         torch.cuda.synchronize()
-        for ctx in ctxs:
-            ctx.shard_accept(colour, st, gathered, world)
+        return torch.cat(locs) if n else None
 
     for ctx in ctxs:
         ctx.init_planes()
-    stage(0, 0)
+    g0 = stage(0, 0, None)
+    for ctx in ctxs:
+        ctx.shard_finish_init(g0, world)
     for _ in range(sc.params.iterations):
         for colour in (0, 1):
+            prev = None
             for st in range(1, n_stages):
-                stage(colour, st)
+                prev = stage(colour, st, prev)
+            stage(colour, n_stages, prev)                  # closing accept of the colour
     outs = []
     for ctx in ctxs:
         ctx.finalize()
@@ -82,8 +87,8 @@ def test_view_shard_color_images():
 
 
 def test_view_shard_runner_single_rank_stream_ordered():
-    """multigpu.ViewShardRunner at world size 1: every stage enqueued on the context's stream (shard_async), no host
-    synchronisation in between — must still equal the fused single-context run bit for bit."""
+    """multigpu.ViewShardRunner at world size 1 = gpm_shard_run: the whole sharded flow enqueued on the context's stream behind
+    the C-ABI, no host synchronisation in between — must equal the fused single-context run bit for bit."""
     from gipuma_b200 import api, multigpu as M, scene as S
     sc = S.make_config(4, rows=96, cols=128, n_views=12, iterations=2, seed=557)
     single, _, _ = api.runcuda(sc, seed=0xC0FFEE)
@@ -103,4 +108,4 @@ def test_view_shard_refuses_other_combinations():
         ctx.load_scene(sc)
         buf = torch.empty(ctx.shard_stage_floats(1), dtype=torch.float32, device="cuda")
         with pytest.raises(api.GipumaError):
-            ctx.shard_eval(0, 1, buf)
+            ctx.shard_stage(0, 1, None, 1, buf)
