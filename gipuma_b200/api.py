@@ -38,6 +38,20 @@ class GpmCamera(C.Structure):
                 ("baseline", C.c_float)]
 
 
+class GpmBatchDesc(C.Structure):
+    _fields_ = [("n_images", C.c_int), ("width", C.c_int), ("height", C.c_int),
+                ("images", C.POINTER(C.c_void_p)), ("pitch_bytes", C.c_size_t), ("P", C.POINTER(C.c_double)),
+                ("cam_scale", C.c_double), ("params", GpmParams), ("min_angle", C.c_float), ("max_angle", C.c_float),
+                ("max_views", C.c_int), ("ref_indices", C.POINTER(C.c_int)), ("n_refs", C.c_int),
+                ("devices", C.POINTER(C.c_int)), ("n_devices", C.c_int), ("seed", C.c_ulonglong),
+                ("out_dir", C.c_char_p), ("out_norm4", C.POINTER(C.c_float)), ("out_cost", C.POINTER(C.c_float))]
+
+
+class GpmBatchStats(C.Structure):
+    _fields_ = [("jobs_done", C.c_int), ("sweep_ms_total", C.c_double), ("per_job_sweep_ms", C.POINTER(C.c_float)),
+                ("per_job_views", C.POINTER(C.c_int)), ("per_job_device", C.POINTER(C.c_int))]
+
+
 class GipumaError(RuntimeError):
     pass
 
@@ -96,13 +110,18 @@ def load_library():
     L.gpm_shard_comm_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     L.gpm_shard_run.argtypes = [vp, fp]
     L.gpm_measure_fetch_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.gpm_debug_packed_mismatches.argtypes = [vp, C.POINTER(C.c_uint), fp, C.c_int]
+    L.gpm_batch_run.argtypes = [C.POINTER(GpmBatchDesc), C.POINTER(GpmBatchStats)]
+    L.gpm_batch_last_error.restype = C.c_char_p
+    L.gpm_shard_p2p_export.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
+    L.gpm_shard_p2p_attach.argtypes = [vp, vp, C.POINTER(vp), C.c_int, C.c_int]
     L.gpm_stream.restype = vp
     for name in ("gpm_create", "gpm_set_params", "gpm_set_reference", "gpm_set_view", "gpm_set_reference_color",
                  "gpm_set_view_color", "gpm_set_num_views",
                  "gpm_set_rng", "gpm_set_state", "gpm_get_state", "gpm_init", "gpm_sweep", "gpm_phase",
                  "gpm_finalize", "gpm_cost_eval", "gpm_run", "gpm_get_stats", "gpm_reset_stats", "gpm_set_option",
                  "gpm_init_planes", "gpm_shard_num_stages", "gpm_shard_stage", "gpm_shard_finish_init", "gpm_shard_unique_id",
-                 "gpm_shard_comm_init", "gpm_shard_comm_attach", "gpm_shard_run", "gpm_measure_fetch_peak",
+                 "gpm_shard_comm_init", "gpm_shard_comm_attach", "gpm_shard_run", "gpm_measure_fetch_peak", "gpm_shard_p2p_export", "gpm_shard_p2p_attach", "gpm_batch_run", "gpm_debug_packed_mismatches",
                  "gpm_prepare_cameras", "gpm_select_views", "gpm_write_dmb", "gpm_read_dmb", "gpm_write_result_dmb"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -296,6 +315,21 @@ class Context:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         self._check(self.lib.gpm_shard_comm_init(self.h, buf, rank, world))
 
+    def shard_p2p_export(self, world: int):
+        """Allocate this rank's peer-memory exchange region; returns (64-byte CUDA IPC handle, device address)."""
+        h = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        self._check(self.lib.gpm_shard_p2p_export(self.h, world, h, C.byref(ptr)))
+        return h.raw, int(ptr.value or 0)
+
+    def shard_p2p_attach(self, handles, rank: int, world: int, local_ptrs=None):
+        """handles: list of `world` 64-byte IPC handles (rank-major); local_ptrs: optional addresses of same-process ranks."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        lp = None
+        if local_ptrs is not None:
+            lp = (C.c_void_p * world)(*[C.c_void_p(p) if p else None for p in local_ptrs])
+        self._check(self.lib.gpm_shard_p2p_attach(self.h, blob, lp, rank, world))
+
     def shard_run(self) -> float:
         """runcuda() with sharded views (gpm_shard_run): returns the sweep time in ms."""
         ms = C.c_float(0)
@@ -307,6 +341,12 @@ class Context:
         self._check(self.lib.gpm_get_stats(self.h, s))
         return {"launches": s[0], "hypotheses": s[1], "skipped": s[2], "pruned": s[3],
                 "pairs": s[4], "pairs_full": s[5], "collectives": s[6]}
+
+    def packed_mismatches(self, reset: bool = True):
+        n = C.c_uint(0)
+        rec = np.zeros((64, 8), np.float32)
+        self._check(self.lib.gpm_debug_packed_mismatches(self.h, C.byref(n), rec.ctypes.data_as(C.POINTER(C.c_float)), int(reset)))
+        return int(n.value), rec[: min(64, int(n.value))]
 
     def measure_fetch_peak(self) -> float:
         """Texture-unit ceiling on this GPU, in 1e9 filtered R32F fetches per second (gpm_measure_fetch_peak)."""
@@ -375,6 +415,40 @@ def select_views(cams, cols: int, rows: int, min_angle: float, max_angle: float,
     if n < 0:
         raise GipumaError("gpm_select_views failed: %d" % n)
     return [sub[i] for i in range(n)], (rng[0], rng[1])
+
+
+def batch_run(images, Ps, params, refs, devices=(0,), cam_scale: float = 1.0, min_angle: float = 10.0, max_angle: float = 30.0,
+              max_views: int = 9, seed: int = 0xC0FFEE, out_dir: Optional[str] = None, want_outputs: bool = True):
+    """Reference-view batch in ONE process (gpm_batch_run): `images` [n, H, W] float32 (shared, page-locked once), `Ps` n 3x4
+    projections, `refs` the reference views to process, `devices` the CUDA ordinals to use (one worker thread each).
+    Returns (norm4 [len(refs), H, W, 4] or None, cost or None, stats dict)."""
+    lib = load_library()
+    imgs = np.ascontiguousarray(images, dtype=np.float32)
+    n, H, W = imgs.shape
+    ptrs = (C.c_void_p * n)(*[C.c_void_p(imgs[i].ctypes.data) for i in range(n)])
+    P = np.ascontiguousarray(np.stack([np.asarray(p, dtype=np.float64) for p in Ps]).reshape(-1))
+    refs_a = (C.c_int * len(refs))(*[int(r) for r in refs])
+    devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+    n4 = np.empty((len(refs), H, W, 4), np.float32) if want_outputs else None
+    cc = np.empty((len(refs), H, W), np.float32) if want_outputs else None
+    d = GpmBatchDesc()
+    d.n_images, d.width, d.height = n, W, H
+    d.images, d.pitch_bytes = ptrs, 0
+    d.P, d.cam_scale = P.ctypes.data_as(C.POINTER(C.c_double)), float(cam_scale)
+    d.params = pack_params(params)
+    d.min_angle, d.max_angle, d.max_views = float(min_angle), float(max_angle), int(max_views)
+    d.ref_indices, d.n_refs, d.devices, d.n_devices, d.seed = refs_a, len(refs), devs, len(devices), seed
+    d.out_dir = out_dir.encode() if out_dir else None
+    d.out_norm4 = n4.ctypes.data_as(C.POINTER(C.c_float)) if want_outputs else None
+    d.out_cost = cc.ctypes.data_as(C.POINTER(C.c_float)) if want_outputs else None
+    ms = (C.c_float * len(refs))()
+    nv = (C.c_int * len(refs))()
+    dv = (C.c_int * len(refs))()
+    st = GpmBatchStats(0, 0.0, ms, nv, dv)
+    rc = lib.gpm_batch_run(C.byref(d), C.byref(st))
+    if rc != 0:
+        raise GipumaError("gpm_batch_run failed (%d): %s" % (rc, lib.gpm_batch_last_error().decode()))
+    return n4, cc, {"jobs_done": st.jobs_done, "sweep_ms_total": st.sweep_ms_total, "sweep_ms": list(ms), "views": list(nv), "device": list(dv)}
 
 
 def write_dmb(path: str, data: np.ndarray):

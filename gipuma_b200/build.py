@@ -35,14 +35,14 @@ def _run(cmd):
 
 
 def build_library(force: bool = False) -> str:
-    src = [os.path.join(HERE, "csrc", f) for f in ("gpm_api.cu", "gpm_host.cpp", "gpm_kernels.cuh", "gpm_device.cuh")]
+    src = [os.path.join(HERE, "csrc", f) for f in ("gpm_api.cu", "gpm_host.cpp", "gpm_batch.cpp", "gpm_kernels.cuh", "gpm_device.cuh")]
     src.append(os.path.join(ROOT, "include", "gipuma_b200.h"))
     out = os.path.join(HERE, "libgipuma_b200.so")
     stamp = out + ".sig"
     sig = _sig(src, " ".join(COMMON))
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == sig:
         return out
-    _run([NVCC] + COMMON + ["-o", out, src[0], src[1]])
+    _run([NVCC] + COMMON + ["-o", out, src[0], src[1], src[2], "-lpthread"])
     with open(stamp, "w") as fh:
         fh.write(sig)
     return out

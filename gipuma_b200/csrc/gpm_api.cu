@@ -59,6 +59,17 @@ struct gpm_ctx {
     bool comm_owned = false;
     int shard_rank = 0, shard_world = 0;
     unsigned long long collectives = 0;
+    // fused peer-memory exchange (k_shard_fused): this rank's region, the peers' regions as mapped here, sequence counter
+    char* p2p_region = nullptr;
+    size_t p2p_bytes = 0, p2p_slot_floats = 0, p2p_flag_bytes = 0;
+    int p2p_world = 0, p2p_nblocks = 0;
+    bool p2p_attached = false;
+    void* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_ipc_opened[8] = {false, false, false, false, false, false, false, false};
+    unsigned p2p_seq = 0;
+    int opt_exchange = 1;
+    int opt_async_upload = 0;                    // 1: image uploads return without a host synchronisation (caller keeps its buffers alive until the next run)
+    bool inputs_dirty = false;                   // an input changed: stored costs / memo are stale (cleared once, at the next launch)                        // 1: peer-memory exchange when attached; 0: NCCL all-gather per stage
     float4* seen = nullptr;          // [H*W*ncand] last plane offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
     int seen_slots = 8;
     float4* refseen = nullptr;       // [H*W]   plane from which the last all-rejected refinement started
@@ -147,6 +158,11 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     if (c->V < 1) return fail(GPM_E_STATE, "no source views (gpm_set_num_views)");
     for (int v = 0; v < c->V; v++)
         if (!c->have_view[v]) return fail(GPM_E_STATE, "source view " + std::to_string(v) + " has not been set");
+    if (c->inputs_dirty) {                 // one clearing for a whole scene upload instead of two memsets per image
+        CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
+        c->inputs_dirty = false;
+    }
     const gpm_params& p = c->prm;
     memset(&P, 0, sizeof(P));
     P.W = c->W;  P.H = c->H;  P.V = c->V;
@@ -157,7 +173,10 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     P.ns_pad = (P.ns + 3) & ~3;
     P.halo = (box + 1) / 2;                                 // gipuma.cu:1844-1847
     P.tile_w = GPM_TILE + 2 * P.halo;
-    P.tile_stride = (P.tile_w + 15) & ~15;                  // 48 or 64 texels: TMA box rows of 192 / 256 bytes (176- and 240-byte rows fault on B200)
+    P.tile_stride = (P.tile_w + 15) & ~15;                  // 48 or 64 texels per staged row
+    // a TMA box must start on a 16-byte boundary of the image (boxes starting at byte offsets 12, 28, 40, 44 fault on B200,
+    // profiles/r02_tma_alignment.txt): tile_x0 + GPM_APRON = 32 bx + 16 - halo, so the box starts (16 - halo) mod 4 texels early
+    P.tile_xo = (c->color == 1) ? 0 : ((GPM_APRON - P.halo) & 3);
     // rounds of 32 consecutive samples (one per lane); the remainder forms a last, shorter round.  A window with
     // fewer than 48 samples (b <= 11) is split into two equal rounds instead.
     {
@@ -385,8 +404,11 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaFuncSetAttribute(k_cost_eval<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_cost_eval<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_shard_stage<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_shard_stage<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
         ok(cudaFuncSetAttribute(k_shard_stage<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
+        ok(cudaFuncSetAttribute(k_shard_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->smem_optin));
     }
     if (err != cudaSuccess) {
         std::string m = std::string("gpm_create: ") + cudaGetErrorString(err);
@@ -405,6 +427,8 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     DeviceGuard g(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && c->comm_owned) gpm_shard_comm_destroy_(c);
+    for (int r = 0; r < 8; r++) if (c->p2p_ipc_opened[r] && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+    cudaFree(c->p2p_region);
     if (c->srcTex) cudaDestroyTextureObject(c->srcTex);
     if (c->srcArr) cudaFreeArray(c->srcArr);
     if (c->srcTex4) cudaDestroyTextureObject(c->srcTex4);
@@ -442,11 +466,7 @@ extern "C" int gpm_set_params(gpm_ctx* c, const gpm_params* p)
 extern "C" int gpm_set_num_views(gpm_ctx* c, int n)
 {
     if (!c || n < 1 || n > c->maxV) return fail(GPM_E_ARG, "gpm_set_num_views: out of range");
-    if (n != c->V) {                       // the cost function changes with the view count: stored costs / memo are stale
-        DeviceGuard g(c->device);
-        CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
-        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
-    }
+    if (n != c->V) c->inputs_dirty = true;           // the cost function changes with the view count: stored costs / memo are stale
     c->V = n;
     return GPM_OK;
 }
@@ -479,9 +499,8 @@ extern "C" int gpm_set_reference(gpm_ctx* c, const float* img, size_t pitch_byte
     k_pad_reference<<<gr, b, 0, c->stream>>>(d, pf, c->W, c->H, c->refpad, c->refpitch, c->refrows);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
-    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
-    CU(cudaStreamSynchronize(c->stream));     // staging buffer is reused by the next upload
+    c->inputs_dirty = true;
+    if (!c->opt_async_upload) CU(cudaStreamSynchronize(c->stream));     // the caller may reuse its buffer
     return GPM_OK;
 }
 
@@ -494,14 +513,22 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     size_t pf = 0;
     int rc = ensure_color(c, 0);
     if (rc) return rc;
-    rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);          // host images go through the staging buffer
-    if (rc) return rc;
     cudaMemcpy3DParms m;  memset(&m, 0, sizeof(m));
-    m.srcPtr = make_cudaPitchedPtr(d, pf * sizeof(float), c->W, c->H);
     m.dstArray = c->srcArr;
     m.dstPos = make_cudaPos(0, 0, v);
     m.extent = make_cudaExtent(c->W, c->H, 1);
-    m.kind = cudaMemcpyDeviceToDevice;
+    if (!on_device && !c->opt_packed) {
+        // host image straight into its layer of the array: no staging copy
+        const size_t pb = pitch_bytes ? pitch_bytes : (size_t)c->W * sizeof(float);
+        if (pb % sizeof(float)) return fail(GPM_E_ARG, "pitch_bytes must be a multiple of 4");
+        m.srcPtr = make_cudaPitchedPtr(const_cast<float*>(img), pb, c->W, c->H);
+        m.kind = cudaMemcpyHostToDevice;
+    } else {
+        rc = upload_image(c, img, pitch_bytes, on_device, &d, &pf);      // staging buffer (the gradient planes of the packed mode read it)
+        if (rc) return rc;
+        m.srcPtr = make_cudaPitchedPtr(d, pf * sizeof(float), c->W, c->H);
+        m.kind = cudaMemcpyDeviceToDevice;
+    }
     CU(cudaMemcpy3DAsync(&m, c->stream));
     c->view_8bit[v] = 0;
     if (c->opt_packed) {                         // experimental packed sampling mode: central-difference planes + "8-bit valued" test
@@ -535,9 +562,8 @@ extern "C" int gpm_set_view(gpm_ctx* c, int v, const float* img, size_t pitch_by
     memcpy(vc.t, cam->t, sizeof(vc.t));
     c->cams_dirty = true;
     c->have_view[v] = 1;
-    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
-    CU(cudaStreamSynchronize(c->stream));        // staging buffers are reused; the caller may reuse its buffer
+    c->inputs_dirty = true;
+    if (!c->opt_async_upload) CU(cudaStreamSynchronize(c->stream));        // the caller may reuse its buffer
     return GPM_OK;
 }
 
@@ -589,9 +615,8 @@ extern "C" int gpm_set_reference_color(gpm_ctx* c, const float* rgba, size_t pit
     k_pad_reference4<<<gr, b, 0, c->stream>>>(d, pe, c->W, c->H, c->refpad4, c->refpitch, c->refrows);
     CU(cudaGetLastError());
     set_ref_camera(c, cam);
-    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    c->inputs_dirty = true;
+    if (!c->opt_async_upload) CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
 
@@ -625,9 +650,8 @@ extern "C" int gpm_set_view_color(gpm_ctx* c, int v, const float* rgba, size_t p
     c->cams_dirty = true;
     c->have_view[v] = 1;
     c->view_8bit[v] = 0;
-    CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));
-    CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    c->inputs_dirty = true;
+    if (!c->opt_async_upload) CU(cudaStreamSynchronize(c->stream));
     return GPM_OK;
 }
 
@@ -1014,6 +1038,99 @@ static int shard_exchange(gpm_ctx* c, int stage)
     return GPM_OK;
 }
 
+// ---- fused peer-memory exchange: region management ------------------------------------------------------------------
+static dim3 shard_grid(gpm_ctx* c)
+{
+    dim3 grid((c->W + GPM_TILE - 1) / GPM_TILE, (c->H + GPM_TILE - 1) / GPM_TILE);
+    int split = 1;                                        // at least ~8 waves of blocks, as in launch_colour
+    while (split < 8 && (long long)grid.x * grid.y * split < 8LL * c->num_sms) split *= 2;
+    grid.z = split;
+    return grid;
+}
+
+// Allocate this rank's exchange region for a shard group of `world` ranks and return its CUDA IPC handle (64 bytes) and its
+// address (for ranks living in the same process).  Layout: [world][nblocks] arrival flags, then [2][world][slot] lists.
+extern "C" int gpm_shard_p2p_export(gpm_ctx* c, int world, void* handle64, void** local_ptr)
+{
+    if (!c || world < 2 || world > 8) return fail(GPM_E_ARG, "gpm_shard_p2p_export: bad arguments (2 <= world <= 8)");
+    if (!c->have_params) return fail(GPM_E_STATE, "gpm_shard_p2p_export: parameters not set");
+    DeviceGuard g(c->device);
+    long long mx = 0;
+    const int ns = gpm_shard_num_stages(c);
+    for (int st = 0; st < ns; st++) { const long long f = gpm_shard_stage_floats(c, st);  if (f > mx) mx = f; }
+    const dim3 grid = shard_grid(c);
+    const int nblocks = (int)(grid.x * grid.y * grid.z);
+    const size_t flag_bytes = ((size_t)world * nblocks * sizeof(unsigned) + 1023) & ~(size_t)1023;
+    const size_t bytes = flag_bytes + 2ull * world * (size_t)mx * sizeof(float);
+    if (!c->p2p_region || c->p2p_bytes != bytes || c->p2p_world != world) {
+        CU(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < 8; r++) { if (c->p2p_ipc_opened[r] && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);  c->p2p_peer[r] = nullptr;  c->p2p_ipc_opened[r] = false; }
+        cudaFree(c->p2p_region);  c->p2p_region = nullptr;  c->p2p_attached = false;
+        CU(cudaMalloc(&c->p2p_region, bytes));
+        c->p2p_bytes = bytes;  c->p2p_world = world;
+    }
+    c->p2p_slot_floats = (size_t)mx;  c->p2p_flag_bytes = flag_bytes;  c->p2p_nblocks = nblocks;
+    CU(cudaMemsetAsync(c->p2p_region, 0, flag_bytes, c->stream));          // flags: nothing has arrived
+    CU(cudaStreamSynchronize(c->stream));
+    c->p2p_seq = 0;
+    if (handle64) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->p2p_region));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle64, &h, 64);
+    }
+    if (local_ptr) *local_ptr = c->p2p_region;
+    return GPM_OK;
+}
+
+// Map the regions of all ranks of the group.  `handles64`: world x 64 bytes (rank-major) from gpm_shard_p2p_export of every
+// rank, opened with cudaIpcOpenMemHandle (ranks in other processes); `local_ptrs` (may be NULL): world addresses, a non-NULL
+// entry is used as is (ranks in this process).  Every rank must have exported before any rank attaches.
+extern "C" int gpm_shard_p2p_attach(gpm_ctx* c, const void* handles64, void* const* local_ptrs, int rank, int world)
+{
+    if (!c || world < 2 || world > 8 || rank < 0 || rank >= world) return fail(GPM_E_ARG, "gpm_shard_p2p_attach: bad arguments");
+    if (!c->p2p_region || c->p2p_world != world) return fail(GPM_E_STATE, "gpm_shard_p2p_attach: call gpm_shard_p2p_export(ctx, world, ...) first");
+    DeviceGuard g(c->device);
+    for (int r = 0; r < world; r++) {
+        if (c->p2p_ipc_opened[r] && c->p2p_peer[r]) cudaIpcCloseMemHandle(c->p2p_peer[r]);
+        c->p2p_peer[r] = nullptr;  c->p2p_ipc_opened[r] = false;
+        if (r == rank) { c->p2p_peer[r] = c->p2p_region;  continue; }
+        if (local_ptrs && local_ptrs[r]) { c->p2p_peer[r] = local_ptrs[r];  continue; }
+        if (!handles64) return fail(GPM_E_ARG, "gpm_shard_p2p_attach: no handle for a peer");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles64 + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->p2p_peer[r] = ptr;  c->p2p_ipc_opened[r] = true;
+    }
+    c->shard_rank = rank;  c->shard_world = world;  c->p2p_attached = true;
+    return GPM_OK;
+}
+
+static int shard_launch_fused(gpm_ctx* c, const KParams& P, int colour, int init_phase, int exchanges)
+{
+    const int last = 1 + shard_refine_steps(c->prm);
+    const dim3 grid = shard_grid(c);
+    ShardState S{c->dispbuf, c->candbuf, c->canddepth, c->sflags};
+    ShardP2P X;
+    memset(&X, 0, sizeof(X));
+    for (int r = 0; r < c->shard_world; r++) {
+        X.flags[r] = reinterpret_cast<unsigned*>(c->p2p_peer[r]);
+        X.lists[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(c->p2p_peer[r]) + c->p2p_flag_bytes);
+    }
+    X.err = reinterpret_cast<unsigned*>(c->d_stats + 7);
+    X.slot_floats = c->p2p_slot_floats;  X.me = c->shard_rank;  X.world = c->shard_world;  X.nblocks = c->p2p_nblocks;
+    auto kern = P.color ? k_shard_fused<false, true> : (P.packed ? k_shard_fused<true, false> : k_shard_fused<false, false>);
+    kern<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad,
+        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, c->seen, c->refseen, c->memo_mask, colour, init_phase, last,
+        X, c->p2p_seq, c->opt_stats ? c->d_stats : nullptr);
+    c->launches++;
+    c->p2p_seq += (unsigned)exchanges;
+    c->collectives += (unsigned long long)exchanges;
+    CU(cudaGetLastError());
+    return GPM_OK;
+}
+
 // runcuda() with the source views sharded over the ranks of the attached communicator.  Every rank calls it with the same
 // parameters, reference image and seed and ITS views; all work — kernels and collectives — is enqueued on the context's
 // stream, one host synchronisation at the end.
@@ -1032,6 +1149,35 @@ extern "C" int gpm_shard_run(gpm_ctx* c, float* sweep_ms)
     const int world = c->shard_world, last = 1 + shard_refine_steps(c->prm);
     CU(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
     c->launches = 0;  c->collectives = 0;
+    if (world > 1 && c->p2p_attached && c->opt_exchange == 1) {
+        // fused flow: one launch for the initial costs, one per colour pass; the exchange happens inside the kernels
+        dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
+        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr);
+        c->launches++;
+        CU(cudaGetLastError());
+        rc = shard_launch_fused(c, P0, 0, 1, 1);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
+        CU(cudaEventRecord(c->ev0, c->stream));
+        for (int it = 0; it < c->prm.iterations; it++)
+            for (int colour = 0; colour < 2; colour++) {
+                rc = shard_launch_fused(c, P, colour, 0, last);
+                if (rc) return rc;
+            }
+        rc = do_finalize(c);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaEventSynchronize(c->ev1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (sweep_ms) *sweep_ms = ms;
+        unsigned long long err = 0;
+        CU(cudaMemcpyAsync(&err, c->d_stats + 7, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (err & 0xffffffffull) return fail(GPM_E_STATE, "gpm_shard_run: a peer rank did not deliver its lists in time (peer-memory exchange)");
+        return GPM_OK;
+    }
+    if (world > 1 && !c->comm) return fail(GPM_E_STATE, "gpm_shard_run: neither an NCCL communicator nor peer regions are attached");
     {
         dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
         k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr);
@@ -1085,6 +1231,19 @@ extern "C" int gpm_init_planes(gpm_ctx* c)
     CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));      // every plane is new: costs and memo are stale
     CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return GPM_OK;
+}
+
+// diagnostics of the experimental packed sampling mode ("packed" = 3): number of fetches whose one-fetch gradient differed
+// from the reference's four fetches, and up to 64 records {cx, cy, view, gx packed, gx reference, gy packed, gy reference, centre}
+extern "C" int gpm_debug_packed_mismatches(gpm_ctx* c, unsigned* count, float* records512, int reset)
+{
+    if (!c || !count) return fail(GPM_E_ARG, "gpm_debug_packed_mismatches: null argument");
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyFromSymbol(count, g_packed_mismatch_n, sizeof(unsigned)));
+    if (records512) CU(cudaMemcpyFromSymbol(records512, g_packed_mismatch, 64 * 8 * sizeof(float)));
+    if (reset) { const unsigned z = 0;  CU(cudaMemcpyToSymbol(g_packed_mismatch_n, &z, sizeof(z))); }
     return GPM_OK;
 }
 
@@ -1162,6 +1321,8 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "memo") c->opt_memo = value != 0;
     else if (n == "quadperm") c->opt_quadperm = value != 0;
     else if (n == "tma") c->opt_tma = value != 0;
+    else if (n == "exchange") c->opt_exchange = value != 0;
+    else if (n == "async_upload") c->opt_async_upload = value != 0;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

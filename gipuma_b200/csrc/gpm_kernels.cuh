@@ -59,7 +59,7 @@ __device__ __forceinline__ void stage_block(const KParams& P, const CUtensorMap*
         if (threadIdx.x == 0) {
             if (phase == 0u) mbar_init(bar, 1);
             mbar_arrive_expect_tx(bar, (unsigned)(tile_floats(P) * sizeof(float)));
-            tma_load_2d(tile, tmap, (tile_x0 + GPM_APRON) * (P.color ? 4 : 1), tile_y0 + GPM_APRON, bar);
+            tma_load_2d(tile, tmap, (tile_x0 + GPM_APRON - P.tile_xo) * (P.color ? 4 : 1), tile_y0 + GPM_APRON, bar);
         }
     } else if (P.color) {                           // float4 texels: refpitch counts float4 elements
         const float4* src4 = reinterpret_cast<const float4*>(refpad) + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
@@ -72,7 +72,7 @@ __device__ __forceinline__ void stage_block(const KParams& P, const CUtensorMap*
         const float* src = refpad + (size_t)(tile_y0 + GPM_APRON) * P.refpitch + (tile_x0 + GPM_APRON);
         for (int e = threadIdx.x; e < tw * tw; e += blockDim.x) {
             const int J = e / tw, I = e - J * tw;
-            tile[J * ts + I] = src[(size_t)J * P.refpitch + I];
+            tile[J * ts + P.tile_xo + I] = src[(size_t)J * P.refpitch + I];
         }
     }
     const float* c = reinterpret_cast<const float*>(cams);
@@ -161,7 +161,7 @@ k_cost_eval(const __grid_constant__ KParams P, const __grid_constant__ CUtensorM
     for (int idx = warp; idx < GPM_TILE * GPM_TILE; idx += P.nwarps) {
         const int px = blockIdx.x * GPM_TILE + (idx & 31), py = blockIdx.y * GPM_TILE + (idx >> 5);
         if (px >= P.W || py >= P.H) continue;
-        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);
         const float4 n = planes[(size_t)py * P.W + px];
         const float inf = __int_as_float(0x7f800000);
         const float c = (P.cost_rt & 12) ? eval_plane<2, PACKED, COLOR>(P, sCam, ws, src, grad, n.x, n.y, n.z, n.w, inf, lane, st, nullptr, nullptr, (unsigned)P.cost_rt)
@@ -292,7 +292,7 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                                        __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
-                if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+                if (!window_ready) { setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
                 const float c = FUSED ? eval_plane<2, PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st, nullptr, nullptr, site)
                                       : eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nb.x, nb.y, nb.z, nb.w, cost_now, lane, st);
                 if (c < cost_now) {                                                              // :867-871
@@ -320,7 +320,7 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                 }
             }
             if (refine) {
-                if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+                if (!window_ready) { setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
                 const float4 norm_start = norm_now;
                 bool any_accept = false;
                 // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
@@ -412,6 +412,17 @@ struct ShardState {
     unsigned char* sflags;
 };
 
+// Peer-memory exchange (k_shard_fused): every rank owns one exchange region = [2 parities][world source ranks][slot_floats]
+// lists + [world][nblocks] arrival flags; all regions are mapped into every rank's address space (CUDA IPC over NVLink).
+// A rank writes its lists straight into slot `me` of every peer's region and then raises flag [me][block] there.
+struct ShardP2P {
+    float* lists[8];              // list area of rank r's region as mapped here (lists[me] is local memory)
+    unsigned* flags[8];           // flag area of rank r's region
+    unsigned* err;                // local sticky error word (a peer did not arrive in time)
+    unsigned long long slot_floats;
+    int me, world, nblocks;
+};
+
 // merged cost of one slot: the n_best smallest over all ranks' lists, summed ascending, / count  (gipuma.cu:779-803)
 __device__ __forceinline__ float shard_merge(const float* __restrict__ g, size_t rank_stride, int world, int nb)
 {
@@ -476,14 +487,14 @@ __device__ __forceinline__ float4 shard_refine_candidate(const KParams& P, const
 // stage 1: the 8 propagation slots in the reference's order (gipuma.cu:1571-1582, 1450-1462; accept rule :867-871);
 // stage >= 2: one refinement step (:986-990).
 __device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float4* __restrict__ planes, const ShardState& S,
-                                                   int px, int py, int stage, const float* __restrict__ gathered, int world,
+                                                   int px, int py, int stage, const float* __restrict__ gathered, int world, size_t rank_stride,
                                                    float4& norm_now, float& cost_now, float& disp_now, int& prov_now, unsigned& sf,
                                                    unsigned lane)
 {
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
     const size_t center = (size_t)py * W + px;
     const int slots = (stage == 1) ? 8 : 1;
-    const size_t per_rank = (size_t)H * Wh * slots * nb;
+    const size_t per_rank = rank_stride ? rank_stride : (size_t)H * Wh * slots * nb;
     const float* g = gathered + ((size_t)py * Wh + (px >> 1)) * slots * nb;
     const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
     if (stage == 1) {
@@ -517,8 +528,21 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
                                                   const ShardState& S, float4* __restrict__ seen, float4* __restrict__ refseen,
                                                   unsigned* __restrict__ memo_mask, int px, int py, int tile_x0, int tile_y0,
                                                   int stage, int last_stage, const float* __restrict__ gathered_prev, int world,
-                                                  float* __restrict__ xchg, unsigned lane, WarpStats& st)
+                                                  float* __restrict__ xchg, unsigned lane, WarpStats& st,
+                                                  size_t rank_stride = 0, const ShardP2P* X = nullptr, size_t slot_off = 0)
 {
+    // fused exchange: copy this pixel's finished lists (count floats at `o`, just written to the local slot) into slot `me` of
+    // every peer's region — plain stores over NVLink; the block raises the arrival flags after its last pixel
+    auto publish = [&](const float* o, int count) {
+        if (!X) return;
+        __syncwarp();
+        const size_t off = slot_off + (size_t)(o - xchg);
+        for (int i = (int)lane; i < count; i += 32) {
+            const float v = o[i];
+            for (int d = 0; d < X->world; d++)
+                if (d != X->me) X->lists[d][off + i] = v;
+        }
+    };
     const RefCam& cam = P.ref;
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
     const size_t center = (size_t)py * W + px;
@@ -528,9 +552,10 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
     float4 norm_now = planes[center];
     if (stage == 0) {                                       // initial costs (gipuma.cu:1040-1049), both colours: two half-resolution planes
         float* out = xchg + ((size_t)((px + py) & 1) * H * Wh + (size_t)py * Wh + (px >> 1)) * nb;
-        setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+        setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);
         eval_plane<(COLOR ? 1 : 0), PACKED, COLOR>(P, sCam, ws, src, grad, norm_now.x, norm_now.y, norm_now.z, norm_now.w, inf, lane, st, &c0, &c1);
         local_topn(P, c0, c1, lane, out);
+        publish(out, nb);
         return;
     }
     float cost_now = cost[center];
@@ -540,7 +565,7 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
     unsigned mmask = P.memo ? memo_mask[center] : 0u;
     unsigned new_mask = mmask;
     if (stage >= 2) {
-        shard_accept_pixel(P, planes, S, px, py, stage - 1, gathered_prev, world, norm_now, cost_now, disp_now, prov_now, sf, lane);
+        shard_accept_pixel(P, planes, S, px, py, stage - 1, gathered_prev, world, rank_stride, norm_now, cost_now, disp_now, prov_now, sf, lane);
         if (stage == 2) {
             // refinement memo (see k_sweep): the S candidates are a pure function of (pixel, plane at refinement start)
             sf = 0u;
@@ -590,12 +615,13 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
                 skip = !in_range || same_now || __any_sync(GPM_FULL, same_mine);
             }
             if (skip) { st.skip++;  if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
-            if (!window_ready) { setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
+            if (!window_ready) { setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
             eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out + k * nb);
         }
         if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
         new_mask |= (cand_mask & 0xffu);
+        publish(out, 8 * nb);
     } else {
         if (sf & GPM_SF_SKIP_REFINE) {
             st.skip++;
@@ -604,10 +630,11 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
             float depth_new;
             const float4 cand = shard_refine_candidate(P, norm_now, disp_now, fpx, fpy, stage - 2, depth_new);
             if (lane == 0) { S.candbuf[center] = cand;  S.canddepth[center] = depth_new; }
-            setup_window<COLOR>(P, tile, ws, px, py, tile_x0, tile_y0, lane);
+            setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);
             eval_plane<0, PACKED, COLOR>(P, sCam, ws, src, grad, cand.x, cand.y, cand.z, cand.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out);
         }
+        publish(out, nb);
     }
     if (lane == 0) {
         if (stage >= 2) { planes[center] = norm_now;  cost[center] = cost_now;  prov[center] = (unsigned char)prov_now; }
@@ -647,6 +674,99 @@ k_shard_stage(const __grid_constant__ KParams P, const __grid_constant__ CUtenso
         if (px >= P.W || py >= P.H) continue;
         shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, seen, refseen, memo_mask, px, py,
                                          tile_x0, tile_y0, stage, last_stage, gathered_prev, world, xchg, lane, st);
+    }
+    flush_stats(stats, st, lane);
+}
+
+// ---- fused compute + exchange over peer memory (NVLink / NVSwitch) ---------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until every peer has delivered its lists of exchange `seq` for this block (one spinning thread per peer)
+__device__ __forceinline__ void p2p_wait(const ShardP2P& X, unsigned bid, unsigned seq)
+{
+    if ((int)threadIdx.x < X.world && (int)threadIdx.x != X.me) {
+        const unsigned* f = X.flags[X.me] + (size_t)threadIdx.x * X.nblocks + bid;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - seq) < 0) {
+            if (*(volatile unsigned*)X.err) break;
+            if (clock64() - t0 > (1LL << 33)) { atomicExch(X.err, 1u);  break; }      // ~4 s: fail loudly on the host, never hang
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+}
+// all lists of this block are stored: make them visible system-wide, then raise flag [me][bid] = seq at every peer
+__device__ __forceinline__ void p2p_signal(const ShardP2P& X, unsigned bid, unsigned seq)
+{
+    __syncthreads();
+    if ((int)threadIdx.x < X.world && (int)threadIdx.x != X.me) {
+        __threadfence_system();
+        st_release_sys(X.flags[threadIdx.x] + (size_t)X.me * X.nblocks + bid, seq);
+    }
+}
+
+// One whole colour pass (all 1 + S exchange stages and the closing accept) — or, with init_phase, the initial-cost stage and
+// its accept — of one tile slice per block, the exchange fused in: after every stage the block's lists are already in every
+// peer's memory (stored there pixel by pixel while the block was still sampling) and only the arrival flags remain to be
+// raised; before the next stage the block waits for the same block of every peer — never for another block of its own GPU,
+// so blocks need not be co-resident and the transfer of one tile overlaps the sampling of all the others.  The reference
+// window is staged once per colour instead of once per stage.  `seq0` = number of exchanges completed before this launch.
+template <bool PACKED, bool COLOR>
+__global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
+k_shard_fused(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams,
+              const float* __restrict__ refpad, cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes,
+              float* __restrict__ cost, unsigned char* __restrict__ prov, ShardState S, float4* __restrict__ seen,
+              float4* __restrict__ refseen, unsigned* __restrict__ memo_mask, int colour, int init_phase, int last_stage,
+              const __grid_constant__ ShardP2P X, unsigned seq0, unsigned long long* __restrict__ stats)
+{
+    extern __shared__ __align__(128) float smem[];
+    float* tile = smem;
+    float* sCam = tile + tile_floats(P);
+    float* scratch = smem + fixed_smem_floats(P);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
+    const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    stage_block(P, &tmap, refpad, cams, tile, sCam, tile_x0, tile_y0);
+    const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
+    WarpStats st = {0, 0, 0, 0, 0};
+    const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
+    const int npix = init_phase ? GPM_TILE * GPM_TILE : GPM_TILE * GPM_TILE / 2;
+    const int per_slice = (npix + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int idx0 = (int)blockIdx.z * per_slice, idx_end = min(npix, idx0 + per_slice);
+    const int first = init_phase ? 0 : 1, lastS = init_phase ? 0 : last_stage;
+    const size_t slot = (size_t)X.slot_floats;
+    for (int stage = first; stage <= lastS + 1; stage++) {
+        const bool closing = stage > lastS;
+        const unsigned seq = seq0 + (unsigned)(stage - first) + 1u;          // exchange produced by `stage`
+        if (stage > first) p2p_wait(X, bid, seq - 1u);
+        const float* prev = X.lists[X.me] + (size_t)((seq - 1u) & 1u) * X.world * slot;
+        const size_t slot_off = ((size_t)(seq & 1u) * X.world + X.me) * slot;
+        float* outb = X.lists[X.me] + slot_off;
+        for (int idx = idx0 + (int)warp; idx < idx_end; idx += P.nwarps) {
+            int px, py;
+            if (init_phase) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
+            else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }
+            if (px >= W || py >= H) continue;
+            if (init_phase && closing) {                                      // merged initial cost (gipuma.cu:1040-1049 over all views)
+                if (lane == 0) {
+                    const float* g = prev + ((size_t)((px + py) & 1) * H * Wh + (size_t)py * Wh + (px >> 1)) * nb;
+                    cost[(size_t)py * W + px] = shard_merge(g, slot, X.world, nb);
+                    prov[(size_t)py * W + px] = P.color ? 3 : 0;
+                }
+                continue;
+            }
+            shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, seen, refseen, memo_mask, px, py,
+                                             tile_x0, tile_y0, stage, lastS, prev, X.world, outb, lane, st, slot, &X, slot_off);
+        }
+        if (!closing) p2p_signal(X, bid, seq);
     }
     flush_stats(stats, st, lane);
 }

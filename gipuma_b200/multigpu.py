@@ -79,25 +79,12 @@ def merge_topn(gathered: np.ndarray, n_best: int) -> np.ndarray:
 # reference-view batch
 # ----------------------------------------------------------------------------------------------------------------
 
-def run_reference_view_batch(make_scene: Callable[[int], object], n_reference_views: int, rank: int, world: int,
-                             device: int = 0, on_result: Optional[Callable] = None) -> List[float]:
-    """Run this rank's share of the reference views, one after another, on its GPU.  Returns the sweep times (ms)."""
+def run_reference_view_batch(images, Ps, params, refs: Sequence[int], devices: Sequence[int] = (0,), **kw):
+    """The shell loop of scripts/dtu_fast.sh:30-55 in one process: gpm_batch_run (native host C++, gipuma_b200/csrc/gpm_batch.cpp)
+    — a worker thread and context per device, ONE page-locked copy of the image set shared by all of them, reference views
+    taken from a common queue.  Thin wrapper over api.batch_run; returns (norm4, cost, stats)."""
     from . import api
-    times = []
-    ctx = None
-    for ref in assign_reference_views(n_reference_views, rank, world):
-        sc = make_scene(ref)
-        if ctx is None or (ctx.W, ctx.H) != (sc.cols, sc.rows) or ctx.max_views < sc.n_views:
-            if ctx is not None:
-                ctx.close()
-            ctx = api.Context(sc.cols, sc.rows, sc.n_views, device=device)
-        ctx.load_scene(sc)
-        times.append(ctx.run())
-        if on_result is not None:
-            on_result(ref, *ctx.get_state())
-    if ctx is not None:
-        ctx.close()
-    return times
+    return api.batch_run(images, Ps, params, list(refs), devices=list(devices), **kw)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -117,7 +104,7 @@ def hybrid_layout(world: int, shard: int):
 
 
 def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank: int, world: int, shard: int,
-               device: int = 0, on_result: Optional[Callable] = None) -> List[float]:
+               device: int = 0, on_result: Optional[Callable] = None, exchange: str = "p2p") -> List[float]:
     """Reference views are dealt round-robin to world/shard groups; inside a group the source views are sharded and
     combined with one all-gather per stage over the group's own communicator.  Returns wall seconds per reference view."""
     import time
@@ -129,7 +116,7 @@ def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank
     times = []
     for ref in assign_reference_views(n_reference_views, my_group, len(members)):
         sc = make_scene(ref)
-        runner = ViewShardRunner(sc, rank_in[rank], shard, device=device, group=groups[my_group])
+        runner = ViewShardRunner(sc, rank_in[rank], shard, device=device, group=groups[my_group], exchange=exchange)
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
         n4, c = runner.run()
@@ -146,11 +133,13 @@ def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank
 # ----------------------------------------------------------------------------------------------------------------
 
 class ViewShardRunner:
-    """One reference view, source views sharded over `world` ranks.  All device work — stage kernels and the NCCL
-    all-gathers — runs behind the C-ABI (gpm_shard_run); torch.distributed is used once, to hand the 128-byte NCCL
-    unique id of the group's rank 0 to the other ranks."""
+    """One reference view, source views sharded over `world` ranks.  All device work runs behind the C-ABI
+    (gpm_shard_run): with exchange="p2p" (default) one fused kernel per colour pass that stores the lists into the peers'
+    memory over NVLink as it samples; with exchange="nccl" one stage kernel + ncclAllGather per exchange stage.
+    torch.distributed is only used at set-up, to pass the NCCL unique id and the CUDA IPC handles around."""
 
-    def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None, options=None):
+    def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None, options=None,
+                 exchange: str = "p2p"):
         from . import api
         self.scene, self.rank, self.world, self.group = scene, rank, world, group
         self.local = partition_views(scene.n_views, world)[rank]
@@ -171,6 +160,16 @@ class ViewShardRunner:
             dist.broadcast_object_list(box, src=src, group=group)
             uid = box[0]
         ctx.shard_comm_init(uid, rank, world)
+        self.exchange = exchange if world > 1 else "none"
+        if world > 1 and exchange == "p2p":
+            # fused compute + exchange over peer memory: swap the CUDA IPC handles of the ranks' exchange regions
+            import torch.distributed as dist
+            handle, _ = ctx.shard_p2p_export(world)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            ctx.shard_p2p_attach(handles, rank, world)
+        elif world > 1:
+            ctx.set_option("exchange", 0)
         self.collectives = 0
 
     def upload(self, scene, images=None):

@@ -151,6 +151,13 @@ int gpm_shard_unique_id(void* id128);
 int gpm_shard_comm_init(gpm_ctx* ctx, const void* id128, int rank, int world);
 int gpm_shard_comm_attach(gpm_ctx* ctx, void* nccl_comm, int rank, int world);
 int gpm_shard_run(gpm_ctx* ctx, float* sweep_ms);
+/* Fused compute + exchange over peer memory (NVLink / NVSwitch), the default of gpm_shard_run once attached: every rank
+ * exports one exchange region (CUDA IPC handle, 64 bytes; `local_ptr` for ranks of the same process), the handles of all
+ * ranks are handed to gpm_shard_p2p_attach, and from then on one kernel per colour pass stores each pixel's lists directly
+ * into the peers' regions while it samples and synchronises tile by tile with arrival flags — no collective launches.
+ * Option "exchange" = 0 falls back to the NCCL all-gather flow. */
+int gpm_shard_p2p_export(gpm_ctx* ctx, int world, void* handle64, void** local_ptr);
+int gpm_shard_p2p_attach(gpm_ctx* ctx, const void* handles64, void* const* local_ptrs, int rank, int world);
 
 /* Counters of the last gpm_sweep/gpm_run: [0] kernels launched, [1] hypotheses offered,
  * [2] hypotheses skipped as exact duplicates / out of depth range, [3] hypotheses cut short by the
@@ -164,6 +171,11 @@ int gpm_reset_stats(gpm_ctx* ctx);
  * bench.py's roofline.binding_unit divides the achieved fetch rate by it. */
 int gpm_measure_fetch_peak(gpm_ctx* ctx, double* gfetch_per_s);
 
+/* Diagnostics of the experimental "packed" sampling mode (option value 3 = sample both ways and compare): number of fetches
+ * whose one-fetch gradient differed from the reference's four fetches and up to 64 records of 8 floats
+ * {x, y, view, gx packed, gx reference, gy packed, gy reference, centre}. */
+int gpm_debug_packed_mismatches(gpm_ctx* ctx, unsigned* count, float* records512, int reset);
+
 /* Tuning / diagnostics; results are bit-identical for every setting.
  * "prune" (1): exact lower-bound early-out; "dedupe" (1): skip bit-identical candidate planes;
  * "trust_state" (0): treat a state loaded with gpm_set_state as cost-consistent; "nwarps" (0 = auto): warps per block;
@@ -173,6 +185,10 @@ int gpm_measure_fetch_peak(gpm_ctx* ctx, double* gfetch_per_s);
  * all six sweep kernels), bit 1 = float4 gradient folding (float4 initialisation = 3); auto = the propagation kernels' form;
  * "shard_async" (0): 1 makes gpm_shard_stage / gpm_shard_finish_init return after enqueueing on gpm_stream() — run the
  * collective on that stream (or order it with events) instead of paying a host synchronisation per stage;
+ * "tma" (1): stage the reference window with one cp.async.bulk.tensor (TMA) per block instead of a cooperative copy;
+ * "exchange" (1): view shard over peer memory when regions are attached, 0 = NCCL all-gather per stage;
+ * "async_upload" (0): 1 lets gpm_set_reference / gpm_set_view return without a host synchronisation — the caller keeps its
+ * (page-locked) image buffers unchanged until the next gpm_run / gpm_sweep returns;
  * "quadperm" (1): deal the samples of a round to the lanes as 2x2 blocks per hardware quad (texture-unit locality);
  * "neighbours" (8): 20 selects the reference's fused sweep — the kernels it launches when built without SMALLKERNEL
  * (gipuma.cu:1122-1351, 1913-1940): 12 axial + 8 knight-move neighbours, then refinement, one launch per colour; bit-exact
@@ -196,6 +212,41 @@ int gpm_select_views(const gpm_camera* cams, int n, int cols, int rows, float mi
 int gpm_write_dmb(const char* path, const float* data, int rows, int cols, int channels);
 int gpm_read_dmb(const char* path, float* data, size_t capacity_floats, int* rows, int* cols, int* channels);
 int gpm_write_result_dmb(const char* depth_path, const char* normal_path, const float* norm4, int rows, int cols);
+
+/* ---- reference-view batch driver: replaces the shell loop that starts one `gipuma` process per
+ * reference image (scripts/dtu_fast.sh:30-55) and the view selection of main.cpp:430-499 ------------------------------
+ * One process, a worker thread + gpm_ctx per listed device, ONE page-locked copy of the image set shared by all of them
+ * (each image is registered once, uploaded asynchronously by whichever device needs it), reference views taken from a
+ * common queue.  Per reference view: cameras re-based on it (gpm_prepare_cameras), source views selected
+ * (gpm_select_views), depth range as main.cpp:480-483 / 898-906, gpm_run, result returned and / or written as
+ * <out_dir>/<ref, 8 digits>/{disp,normals}.dmb (main.cpp:1002-1003) for the external fusibile. */
+typedef struct gpm_batch_desc {
+    int n_images, width, height;
+    const float* const* images;        /* n_images host pointers, row-major float, pitch_bytes between rows (0 = width*4) */
+    size_t pitch_bytes;
+    const double* P;                   /* n_images row-major 3x4 projection matrices */
+    double cam_scale;                  /* --cam_scale (K divided by it); <= 0 means 1 */
+    gpm_params params;                 /* depthMin / depthMax <= 0: taken from the view selection; disparities are derived */
+    float min_angle, max_angle;        /* degrees (scripts/dtu_fast.sh:18-19) */
+    int max_views;                     /* scripts/dtu_fast.sh:21 */
+    const int* ref_indices;            /* reference views to process (NULL: 0 .. n_refs-1) */
+    int n_refs;
+    const int* devices;                /* CUDA device ordinals, one worker each */
+    int n_devices;
+    unsigned long long seed;
+    const char* out_dir;               /* NULL: no files */
+    float* out_norm4;                  /* NULL or n_refs * height*width*4 floats (world normal + depth per job) */
+    float* out_cost;                   /* NULL or n_refs * height*width floats */
+} gpm_batch_desc;
+typedef struct gpm_batch_stats {
+    int jobs_done;
+    double sweep_ms_total;             /* sum of the jobs' device times (reference's own span) */
+    float* per_job_sweep_ms;           /* NULL or n_refs entries */
+    int* per_job_views;                /* NULL or n_refs entries: source views selected */
+    int* per_job_device;               /* NULL or n_refs entries: device that ran the job */
+} gpm_batch_stats;
+int gpm_batch_run(const gpm_batch_desc* desc, gpm_batch_stats* stats);
+const char* gpm_batch_last_error(void);
 
 const char* gpm_last_error(void);
 const char* gpm_version(void);

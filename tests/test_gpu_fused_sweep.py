@@ -113,6 +113,6 @@ def test_view_shard_refuses_the_fused_sweep():
         ctx.init_planes()
         buf = torch.empty(ctx.shard_stage_floats(0), dtype=torch.float32, device="cuda")
         with pytest.raises(api.GipumaError):
-            ctx.shard_eval(0, 0, buf)
+            ctx.shard_stage(0, 0, None, 1, buf)
         with pytest.raises(api.GipumaError):
             ctx.set_option("neighbours", 12)

@@ -109,3 +109,51 @@ def test_view_shard_refuses_other_combinations():
         buf = torch.empty(ctx.shard_stage_floats(1), dtype=torch.float32, device="cuda")
         with pytest.raises(api.GipumaError):
             ctx.shard_stage(0, 1, None, 1, buf)
+
+
+def test_fused_peer_memory_exchange_two_ranks_on_one_gpu():
+    """k_shard_fused (compute + exchange over peer memory) with both ranks living in this process on the same GPU: each rank's
+    kernels store their lists straight into the other rank's exchange region and synchronise tile by tile with arrival flags.
+    The two gpm_shard_run calls must overlap (each waits for the other), hence the threads; the image is small enough for both
+    kernels to be resident at once.  Result: bit-identical to the unsharded run on both ranks, and again on a second run
+    (sequence numbers and parity buffers carry over)."""
+    import threading
+    from gipuma_b200 import api, multigpu as M, scene as S
+    sc = S.make_config(2, rows=64, cols=96, n_views=6, iterations=2, seed=558)
+    sc.params.box_hsize = sc.params.box_vsize = 11
+    single, _, _ = api.runcuda(sc, seed=0xC0FFEE)
+    world = 2
+    parts = M.partition_views(sc.n_views, world)
+    ctxs = []
+    for r in range(world):
+        ctx = api.Context(sc.cols, sc.rows, len(parts[r]))
+        ctx.set_params(sc.params)
+        ctx.set_reference(np.ascontiguousarray(sc.images[0]), sc.cameras[0])
+        for v, pos in enumerate(parts[r]):
+            ctx.set_view(v, np.ascontiguousarray(sc.images[sc.subset[pos]]), sc.cameras[sc.subset[pos]])
+        ctx.set_num_views(len(parts[r]))
+        ctx.set_rng(0xC0FFEE)
+        ctxs.append(ctx)
+    exported = [ctx.shard_p2p_export(world) for ctx in ctxs]
+    for r, ctx in enumerate(ctxs):
+        ctx.shard_p2p_attach([h for h, _ in exported], r, world, local_ptrs=[p for _, p in exported])
+    for _ in range(2):
+        errs = []
+
+        def work(ctx):
+            try:
+                ctx.shard_run()
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        threads = [threading.Thread(target=work, args=(ctx,)) for ctx in ctxs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=120)
+        assert not errs, errs
+        for ctx in ctxs:
+            n4, c = ctx.get_state()
+            assert bits_equal(n4, single.norm4) == 0 and bits_equal(c, single.c) == 0
+            assert ctx.stats()["collectives"] > 0
+    for ctx in ctxs:
+        ctx.close()

@@ -137,3 +137,27 @@ def test_select_views_is_monotone_in_max_views_and_respects_the_angle_window():
     ang = S.view_angles(S.prepare_cameras(Ps), 1600, 1200)
     for i in prev:
         assert 10.0 <= np.degrees(ang[i]) <= 30.0
+
+
+def test_prepare_cameras_matches_opencv_getCameraParameters_fixture():
+    """f1 pinned: tests/golden/camera_prep_dtu.npz holds what the reference's getCameraParameters
+    (cameraGeometryUtils.h:174-353) computes for the 64 DTU .P files — produced by tools/make_camera_fixture.py, which runs
+    the same OpenCV routines (decomposeProjectionMatrix, Mat::inv LU / SVD, determinant) on float32 matrices through cv2.
+    gpm_prepare_cameras (host C++, double precision, no OpenCV) must reproduce every Camera_cu field to float32 rounding:
+    1e-6 of the field's scale over the rig (the reference's own float32 pipeline is only that precise), for both scale factors."""
+    import os
+    from conftest import GOLDEN_DIR
+    from gipuma_b200 import api
+    z = np.load(os.path.join(GOLDEN_DIR, "camera_prep_dtu.npz"))
+    Ps = [z["P"][i] for i in range(z["P"].shape[0])]
+    for scale, tag in ((1.0, "s1"), (0.5, "s05")):
+        cams = api.prepare_cameras(Ps, scale)
+        assert len(cams) == 64
+        for key in ("K", "K_inv", "R", "t", "C", "M_inv", "R_orig_inv", "P_col34"):
+            ref = z["%s_%s" % (tag, key)]
+            ours = np.stack([np.array(getattr(c, key)[:], np.float32).reshape(ref[0].shape) for c in cams])
+            assert np.abs(ours - ref).max() <= 1e-6 * np.abs(ref).max(), key
+        for key in ("fx", "fy", "f", "alpha", "baseline"):
+            ref = z["%s_%s" % (tag, key)]
+            ours = np.array([getattr(c, key) for c in cams], np.float32)
+            assert np.abs(ours - ref).max() <= 1e-6 * np.abs(ref).max(), key

@@ -84,6 +84,18 @@ def main():
         key = (it, kind)
         s = stats.setdefault(key, dict(n=0, rejected=0, prefix=0, centre=0, heavy=0, wfrac_prefix=0.0, wfrac_centre=0.0, wfrac_heavy=0.0))
         s["n"] += 1
+        # per-view elimination after the first half (prefix): a view whose partial cost already exceeds the n_best-th smallest
+        # UPPER bound (partial + remaining weight x max dissimilarity) of all views, or n_best x the current cost, cannot enter
+        # the result; how many (view, second-half) evaluations would that save among hypotheses the whole-hypothesis bound keeps?
+        dmax = (1.0 - p.alpha) * p.tau_color + p.alpha * p.tau_gradient
+        lbv = t[:, prefix].sum(axis=1)
+        ubv = lbv + dmax * float(w[~prefix].sum())
+        kth = np.sort(ubv)[min(p.n_best, len(ubv)) - 1]
+        hyp_pruned = combine(lbv, p.n_best) >= cnow
+        dead = (lbv > kth) | (lbv >= p.n_best * cnow)
+        s.setdefault("views_total", 0);  s.setdefault("views_dead", 0);  s.setdefault("hyp_kept", 0)
+        if not hyp_pruned:
+            s["hyp_kept"] += 1;  s["views_total"] += len(lbv);  s["views_dead"] += int(dead.sum())
         if c < cnow:
             return
         s["rejected"] += 1
@@ -142,6 +154,8 @@ def main():
                   "prefix %5.1f%% (weight %.2f)  centre %5.1f%% (%.2f)  heavy %5.1f%% (%.2f)" % (
                       it + 1, kind, s["n"], 100.0 * s["rejected"] / s["n"], 100.0 * s["prefix"] / r, s["wfrac_prefix"] / r,
                       100.0 * s["centre"] / r, s["wfrac_centre"] / r, 100.0 * s["heavy"] / r, s["wfrac_heavy"] / r), flush=True)
+            print("        per-view elimination after the first half: %d hypotheses survive the whole-hypothesis bound; %.1f%% of their views are dead"
+                  % (s.get("hyp_kept", 0), 100.0 * s.get("views_dead", 0) / max(1, s.get("views_total", 0))), flush=True)
 
 
 if __name__ == "__main__":

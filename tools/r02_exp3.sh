@@ -12,6 +12,6 @@ import numpy as np
 print("ok", ms, np.array_equal(a.norm4.view(np.uint32), b_.norm4.view(np.uint32)))
 PY
 done
-timeout 1800 python -m pytest tests -q -m gpu -x --durations=8 2>&1 | tail -16 > $out/pytest_gpu_exp3.log; cat $out/pytest_gpu_exp3.log
+timeout 1800 python -m pytest tests -q -m gpu --durations=8 2>&1 | tail -16 > $out/pytest_gpu_exp3.log; cat $out/pytest_gpu_exp3.log
 timeout 600 python tools/run_shard_nccl.py --config 4 2>&1 | tail -1 | tee $out/exp3_shard_cfg4_1gpu.json | cut -c1-400
 timeout 900 python bench.py --steps 3 --warmup 3 2>$out/bench.err | tail -1 > $out/bench_ours_1gpu.json; cut -c1-400 $out/bench_ours_1gpu.json

@@ -16,6 +16,8 @@ ap.add_argument("--views", type=int, default=None)
 ap.add_argument("--iters", type=int, default=None)
 ap.add_argument("--hybrid", type=int, default=0, help="view-shard width; world/width groups take different reference views")
 ap.add_argument("--refs", type=int, default=2)
+ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="fused peer-memory exchange or one ncclAllGather per stage")
+ap.add_argument("--repeat", type=int, default=2)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -24,7 +26,8 @@ if world > 1:
 if args.hybrid:
     mk = lambda ref: S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters, seed=1234 + 17 * ref)
     outs = {}
-    times = M.run_hybrid(mk, args.refs, rank, world, args.hybrid, device=local, on_result=lambda ref, n4, c: outs.__setitem__(ref, (n4, c)))
+    times = M.run_hybrid(mk, args.refs, rank, world, args.hybrid, device=local, on_result=lambda ref, n4, c: outs.__setitem__(ref, (n4, c)),
+                         exchange=args.exchange)
     ok = True
     for ref, (n4, c) in outs.items():
         single, _, _ = api.runcuda(mk(ref), device=local)
@@ -40,24 +43,34 @@ if args.hybrid:
         dist.barrier(); dist.destroy_process_group()
     sys.exit(0)
 sc = S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters)
-run = M.ViewShardRunner(sc, rank, world, device=local)
+run = M.ViewShardRunner(sc, rank, world, device=local, exchange=args.exchange)
 run.run()                                              # warm-up (NCCL communicator, kernels)
 torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
-t0 = time.perf_counter()
-n4, c = run.run()
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
-t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+best, sweep = 1e30, 1e30
+for _ in range(args.repeat):
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms = run.run_timed()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt, ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    best, sweep = min(best, float(tt[0])), min(sweep, float(tt[1]))
+n4, c = run.ctx.get_state()
+t = torch.tensor([best], dtype=torch.float64, device="cuda")
 out = None
 if rank == 0:
-    single, ms, _ = api.runcuda(sc, device=local)
-    same = np.array_equal(n4.view(np.uint32), single.norm4.view(np.uint32)) and np.array_equal(c.view(np.uint32), single.c.view(np.uint32))
-    out = {"mode": "view_shard", "config": sc.name, "rows": sc.rows, "cols": sc.cols, "views": sc.n_views, "world": world,
-           "wall_s_incl_init": float(t), "mpixel_iters_per_s": sc.rows * sc.cols * sc.params.iterations / 1e6 / float(t),
+    with api.Context(sc.cols, sc.rows, sc.n_views, device=local) as one:
+        one.load_scene(sc)
+        one.run()
+        ms = one.run()
+        s4, s1 = one.get_state()
+    same = np.array_equal(n4.view(np.uint32), s4.view(np.uint32)) and np.array_equal(c.view(np.uint32), s1.view(np.uint32))
+    out = {"mode": "view_shard", "exchange": run.exchange, "config": sc.name, "rows": sc.rows, "cols": sc.cols, "views": sc.n_views, "world": world,
+           "wall_s_incl_init": float(t), "sweep_ms_max_over_ranks": sweep, "single_over_sharded_sweep": ms / sweep, "mpixel_iters_per_s": sc.rows * sc.cols * sc.params.iterations / 1e6 / float(t),
            "single_gpu_sweep_ms": ms, "bit_identical_to_single_gpu": bool(same), "collectives": run.collectives}
 if world > 1:
     dist.barrier()
