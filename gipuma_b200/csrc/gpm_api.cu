@@ -68,6 +68,7 @@ struct gpm_ctx {
     bool p2p_ipc_opened[8] = {false, false, false, false, false, false, false, false};
     unsigned p2p_seq = 0;
     int opt_exchange = 1;
+    int opt_equal_rounds = 0;
     int opt_async_upload = 0;                    // 1: image uploads return without a host synchronisation (caller keeps its buffers alive until the next run)
     bool inputs_dirty = false;                   // an input changed: stored costs / memo are stale (cleared once, at the next launch)                        // 1: peer-memory exchange when attached; 0: NCCL all-gather per stage
     float4* seen = nullptr;          // [H*W*ncand] last plane offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
@@ -177,11 +178,12 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     // a TMA box must start on a 16-byte boundary of the image (boxes starting at byte offsets 12, 28, 40, 44 fault on B200,
     // profiles/r02_tma_alignment.txt): tile_x0 + GPM_APRON = 32 bx + 16 - halo, so the box starts (16 - halo) mod 4 texels early
     P.tile_xo = (c->color == 1) ? 0 : ((GPM_APRON - P.halo) & 3);
-    // rounds of 32 consecutive samples (one per lane); the remainder forms a last, shorter round.  A window with
-    // fewer than 48 samples (b <= 11) is split into two equal rounds instead.
+    // rounds of 32 consecutive samples (one per lane); the remainder forms a last, shorter round whose (view, sample) pairs
+    // are packed several views to an instruction.  (Option "equal_rounds": windows with 33..47 samples — blocksize 11 —
+    // as two equal rounds, the round-1 arrangement; 32 + 4 keeps whole 2x2 quads and measured faster)
     {
         int r = 0;
-        if (P.ns > 32 && P.ns < 48) {
+        if (P.ns > 32 && P.ns < 48 && c->opt_equal_rounds) {
             P.round_end[r++] = (unsigned char)((P.ns + 1) / 2);
             P.round_end[r++] = (unsigned char)P.ns;
         } else {
@@ -1323,6 +1325,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "tma") c->opt_tma = value != 0;
     else if (n == "exchange") c->opt_exchange = value != 0;
     else if (n == "async_upload") c->opt_async_upload = value != 0;
+    else if (n == "equal_rounds") c->opt_equal_rounds = value != 0;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

@@ -493,7 +493,10 @@ __device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float
 {
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
     const size_t center = (size_t)py * W + px;
-    const int slots = (stage == 1) ? 8 : 1;
+    // list layout: NCCL flow — dense per stage (8 slots per pixel in stage 1, 1 otherwise); fused flow (rank_stride != 0) — a
+    // fixed 8 slots per pixel in every stage, so that a pixel's lists only ever alias lists of the same pixel, i.e. of the
+    // same block (blocks of one launch run stages apart from each other; only same-index blocks are ordered by the flags)
+    const int slots = (stage == 1 || rank_stride) ? 8 : 1;
     const size_t per_rank = rank_stride ? rank_stride : (size_t)H * Wh * slots * nb;
     const float* g = gathered + ((size_t)py * Wh + (px >> 1)) * slots * nb;
     const float fpx = __int2float_rn(px), fpy = __int2float_rn(py);
@@ -575,7 +578,7 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
             }
         }
     }
-    float* out = xchg + ((size_t)py * Wh + (px >> 1)) * (stage == 1 ? 8 : 1) * nb;
+    float* out = xchg + ((size_t)py * Wh + (px >> 1)) * ((stage == 1 || rank_stride) ? 8 : 1) * nb;      // see shard_accept_pixel
     if (stage > last_stage) {                               // closing pass of a colour: only the accept of the last refinement step
         if (P.memo && P.rng_mode == 0 && !(sf & (GPM_SF_SKIP_REFINE | GPM_SF_ACCEPTED))) new_mask |= GPM_MEMO_REFINE;
     } else if (stage == 1) {
