@@ -15,6 +15,7 @@ occluding blocks, a texture-less band and sensor noise):
                            parameters) whose source views are sharded over the N ranks; after every exchange stage the ranks'
                            local top-n_best view costs are all-gathered over NCCL/NVLink (gpm_shard_run, behind the C-ABI)
                            and combined exactly as pmCostMultiview_cu does (gipuma.cu:742-806).  "scaling": "strong".
+                           Default exchange: fused into the stage kernels over peer memory (NVLink); --exchange nccl: all-gather.
                            Rank 0 also runs the same job unsharded and reports whether the outputs are bit-identical.
   --mode batch             every rank its own reference view (scripts/dtu_fast.sh:30-55), no collective, weak scaling.
   --mode hybrid --shard G  BASELINE configs[4]: N/G groups, each one 3200x2400 / 64-view reference view sharded G ways.
@@ -137,7 +138,7 @@ def config_dict(args, mode, config, shard, world, sc_name, W, H, V, iters, box, 
         suffix += ", hard scene (occluders, texture-less band, sensor noise)"
     par = {"single": "one reference view on one GPU",
            "batch": "reference-view batch: one independent reference view per GPU, no collective",
-           "view_shard": "one reference view, source views sharded over the GPUs, NCCL all-gather of the local top-n_best view costs per stage",
+           "view_shard": "one reference view, source views sharded over the GPUs; per exchange stage every rank's local top-n_best view costs reach all ranks (fused peer-memory exchange over NVLink, or NCCL all-gather with --exchange nccl)",
            "hybrid": "groups of %d GPUs shard the source views of their group's reference view; groups are independent" % shard}[mode]
     return {"workload": "%s: %s, %dx%d, %d source views, %d iterations, blocksize %d, n_best %d" % (config_label(config), sc_name, W, H, V, iters, box, n_best) + suffix,
             "mode": mode, "parallelism": par,
@@ -363,7 +364,7 @@ def run_ours_sharded(args, mode, config, shard, rank, world, local, sc):
     out4 = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     outc = torch.empty((H, W), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    runner = M.ViewShardRunner(sc, my_rank, shard, device=local, group=group)
+    runner = M.ViewShardRunner(sc, my_rank, shard, device=local, group=group, exchange=args.exchange)
     ctx = runner.ctx
 
     def barrier():
@@ -445,7 +446,9 @@ def run_ours_sharded(args, mode, config, shard, rank, world, local, sc):
             "e2e": {"value": units / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cnt[2].item()),
                     "d2h_bytes_per_step": int(n_groups * W * H * 20), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(cnt[0].item()),
-            "collective": {"kind": "ncclAllGather (gpm_shard_run, behind the C-ABI)", "per_step_per_rank": int(collectives // max(1, args.steps)),
+            "collective": {"kind": {"p2p": "fused in the stage kernels: lists stored into every peer's memory over NVLink (CUDA IPC) + per-tile arrival flags, no collective launches (gpm_shard_run / k_shard_fused)",
+                                    "nccl": "one ncclAllGather per exchange stage (gpm_shard_run, NCCL loaded behind the C-ABI)", "none": "single rank"}[runner.exchange],
+                           "exchange": runner.exchange, "exchanges_per_step_per_rank": int(collectives // max(1, args.steps)),
                            "ranks_per_group": shard, "groups": n_groups},
             "bit_identical_to_single_gpu": identical,
             "strong_scaling": {"single_gpu_value_same_job": single_value, "speedup": (value / n_groups / single_value) if single_value else None,
@@ -531,6 +534,7 @@ def main():
     ap.add_argument("--config", type=int, default=0, help="1-5: BASELINE.json configs; 6: 1600x1200 / 60 views (default of view_shard)")
     ap.add_argument("--shard", type=int, default=0, help="hybrid: GPUs per reference view")
     ap.add_argument("--scene", default="smooth", choices=["smooth", "hard"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sharded modes: fused peer-memory exchange or NCCL all-gather per stage")
     ap.add_argument("--no-check", action="store_true", help="sharded modes: skip the unsharded comparison run on rank 0")
     ap.add_argument("--color", action="store_true", help="float4 images (the reference's -color_processing)")
     ap.add_argument("--neighbours", type=int, default=8, choices=[8, 20],

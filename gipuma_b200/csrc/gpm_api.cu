@@ -69,11 +69,14 @@ struct gpm_ctx {
     unsigned p2p_seq = 0;
     int opt_exchange = 1;
     int opt_equal_rounds = 0;
+    int opt_fused_warps = 8;                     // warps per block of k_shard_fused: 8 -> two blocks per SM, one samples while the other waits for its peers
     int opt_async_upload = 0;                    // 1: image uploads return without a host synchronisation (caller keeps its buffers alive until the next run)
     bool inputs_dirty = false;                   // an input changed: stored costs / memo are stale (cleared once, at the next launch)                        // 1: peer-memory exchange when attached; 0: NCCL all-gather per stage
-    float4* seen = nullptr;          // [H*W*ncand] last plane offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
+    unsigned* seen = nullptr;        // [H*W*ncand] identity of the plane last offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
     int seen_slots = 8;
-    float4* refseen = nullptr;       // [H*W]   plane from which the last all-rejected refinement started
+    unsigned* refseen = nullptr;     // [H*W]   identity of the plane from which the last all-rejected refinement started
+    unsigned* pid = nullptr;         // [H*W]   identity of the stored plane (gpm_kernels.cuh, struct Memo)
+    unsigned* next_id = nullptr;     // device counter of fresh identities
     unsigned* memo_mask = nullptr;   // [H*W] validity bits of seen (0-19) and refseen (GPM_MEMO_REFINE)
     unsigned char* prov = nullptr;   // per pixel: which rounding variant of the cost function produced cost[] (see k_sweep)
     float* refpad = nullptr;
@@ -281,6 +284,22 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     return GPM_OK;
 }
 
+// identities 1 .. W*H belong to the pixels' initial planes; fresh ones start above
+int reset_next_id(gpm_ctx* c)
+{
+    const unsigned first = (unsigned)((size_t)c->W * c->H) + 1u;
+    CU(cudaMemcpyAsync(c->next_id, &first, sizeof(first), cudaMemcpyHostToDevice, c->stream));
+    return GPM_OK;
+}
+
+int fill_ids(gpm_ctx* c)
+{
+    const unsigned n = (unsigned)((size_t)c->W * c->H);
+    k_fill_ids<<<(n + 255) / 256, 256, 0, c->stream>>>(c->pid, n);
+    CU(cudaGetLastError());
+    return reset_next_id(c);
+}
+
 int sync_cams(gpm_ctx* c)
 {
     if (!c->cams_dirty) return GPM_OK;
@@ -300,7 +319,7 @@ int launch_colour(gpm_ctx* c, const KParams& P, int colour, int mask)
     auto kern = P.ncand == 20 ? (P.color ? k_sweep<false, true, true> : k_sweep<false, false, true>)
                               : (P.color ? k_sweep<false, true, false> : (P.packed ? k_sweep<true, false, false> : k_sweep<false, false, false>));
     kern<<<grid, P.nwarps * 32, smem, c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad, P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->rng,
-                                                      c->prov, c->seen, c->refseen, c->memo_mask, colour, mask, c->opt_stats ? c->d_stats : nullptr);
+                                                      c->prov, Memo{c->pid, c->seen, c->refseen, c->memo_mask, c->next_id}, colour, mask, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
     return GPM_OK;
@@ -370,8 +389,10 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     ok(cudaMalloc(&c->planes, n * sizeof(float4)));
     ok(cudaMalloc(&c->cost, n * sizeof(float)));
     ok(cudaMalloc(&c->prov, n));
-    ok(cudaMalloc(&c->seen, n * 8 * sizeof(float4)));
-    ok(cudaMalloc(&c->refseen, n * sizeof(float4)));
+    ok(cudaMalloc(&c->seen, n * 8 * sizeof(unsigned)));
+    ok(cudaMalloc(&c->refseen, n * sizeof(unsigned)));
+    ok(cudaMalloc(&c->pid, n * sizeof(unsigned)));
+    ok(cudaMalloc(&c->next_id, sizeof(unsigned)));
     ok(cudaMalloc(&c->memo_mask, n * sizeof(unsigned)));
     ok(cudaMalloc(&c->staging, n * sizeof(float)));
     ok(cudaMalloc(&c->d_flag, sizeof(int)));
@@ -384,6 +405,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
         ok(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, n, c->stream));
         ok(cudaMemsetAsync(c->memo_mask, 0, n * sizeof(unsigned), c->stream));
         ok(cudaMemsetAsync(c->d_stats, 0, 8 * sizeof(unsigned long long), c->stream));
+        if (fill_ids(c) != GPM_OK) err = cudaErrorUnknown;
         cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
         ok(cudaMalloc3DArray(&c->srcArr, &desc, make_cudaExtent(width, height, max_views), cudaArrayLayered));
     }
@@ -439,7 +461,7 @@ extern "C" void gpm_destroy(gpm_ctx* c)
     if (c->gradTex) cudaDestroyTextureObject(c->gradTex);
     if (c->gradArr) cudaFreeArray(c->gradArr);
     cudaFree(c->gradLin);  cudaFree(c->d_flag);
-    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->seen);  cudaFree(c->refseen);  cudaFree(c->memo_mask);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->sflags);  cudaFree(c->xchg);  cudaFree(c->gath);  cudaFree(c->refpad);  cudaFree(c->staging);
+    cudaFree(c->planes);  cudaFree(c->cost);  cudaFree(c->prov);  cudaFree(c->seen);  cudaFree(c->refseen);  cudaFree(c->pid);  cudaFree(c->next_id);  cudaFree(c->memo_mask);  cudaFree(c->rng);  cudaFree(c->dispbuf);  cudaFree(c->candbuf);  cudaFree(c->canddepth);  cudaFree(c->sflags);  cudaFree(c->xchg);  cudaFree(c->gath);  cudaFree(c->refpad);  cudaFree(c->staging);
     cudaFree(c->d_cams);  cudaFree(c->d_stats);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -663,7 +685,11 @@ extern "C" int gpm_set_state(gpm_ctx* c, const float* norm4, const float* cost, 
     DeviceGuard g(c->device);
     const size_t n = (size_t)c->W * c->H;
     const cudaMemcpyKind k = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (norm4) CU(cudaMemcpyAsync(c->planes, norm4, n * sizeof(float4), k, c->stream));
+    if (norm4) {
+        CU(cudaMemcpyAsync(c->planes, norm4, n * sizeof(float4), k, c->stream));
+        int rc = fill_ids(c);               // caller-supplied planes: every pixel's plane is its own (equal values are simply not recognised as such)
+        if (rc) return rc;
+    }
     if (cost) CU(cudaMemcpyAsync(c->cost, cost, n * sizeof(float), k, c->stream));
     // provenance of the supplied costs is unknown (GPM_PROV_UNKNOWN) unless the caller vouches that they came from an
     // initialisation / refinement evaluation of exactly these planes ("trust_state": 0)
@@ -693,7 +719,8 @@ static int do_init(gpm_ctx* c)
     rc = sync_cams(c);
     if (rc) return rc;
     dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);                   // gipuma.cu:1870-1875
-    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr);
+    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr, c->pid);
+    { int rc_ = reset_next_id(c);  if (rc_) return rc_; }
     c->launches++;
     CU(cudaGetLastError());
     dim3 grid((P.W + GPM_TILE - 1) / GPM_TILE, (P.H + GPM_TILE - 1) / GPM_TILE);
@@ -890,7 +917,7 @@ static int shard_launch_stage(gpm_ctx* c, const KParams& P, int colour, int stag
     ShardState S{c->dispbuf, c->candbuf, c->canddepth, c->sflags};
     auto kern = P.color ? k_shard_stage<false, true> : (P.packed ? k_shard_stage<true, false> : k_shard_stage<false, false>);
     kern<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad,
-        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, c->seen, c->refseen, c->memo_mask, colour, stage, last,
+        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, Memo{c->pid, c->seen, c->refseen, c->memo_mask, c->next_id}, colour, stage, last,
         gathered_prev, world, xchg, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     CU(cudaGetLastError());
@@ -1123,8 +1150,10 @@ static int shard_launch_fused(gpm_ctx* c, const KParams& P, int colour, int init
     X.err = reinterpret_cast<unsigned*>(c->d_stats + 7);
     X.slot_floats = c->p2p_slot_floats;  X.me = c->shard_rank;  X.world = c->shard_world;  X.nblocks = c->p2p_nblocks;
     auto kern = P.color ? k_shard_fused<false, true> : (P.packed ? k_shard_fused<true, false> : k_shard_fused<false, false>);
-    kern<<<grid, P.nwarps * 32, block_smem_bytes(P), c->stream>>>(P, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad,
-        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, c->seen, c->refseen, c->memo_mask, colour, init_phase, last,
+    KParams Pf = P;                                       // half-size blocks: two per SM (128 registers x 256 threads each)
+    if (c->opt_fused_warps > 0 && c->opt_fused_warps < Pf.nwarps) Pf.nwarps = c->opt_fused_warps;
+    kern<<<grid, Pf.nwarps * 32, block_smem_bytes(Pf), c->stream>>>(Pf, c->tmap, c->d_cams, P.color ? (const float*)c->refpad4 : c->refpad,
+        P.color ? c->srcTex4 : c->srcTex, c->gradTex, c->planes, c->cost, c->prov, S, Memo{c->pid, c->seen, c->refseen, c->memo_mask, c->next_id}, colour, init_phase, last,
         X, c->p2p_seq, c->opt_stats ? c->d_stats : nullptr);
     c->launches++;
     c->p2p_seq += (unsigned)exchanges;
@@ -1154,9 +1183,11 @@ extern "C" int gpm_shard_run(gpm_ctx* c, float* sweep_ms)
     if (world > 1 && c->p2p_attached && c->opt_exchange == 1) {
         // fused flow: one launch for the initial costs, one per colour pass; the exchange happens inside the kernels
         dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
-        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr);
+        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr, c->pid);
         c->launches++;
         CU(cudaGetLastError());
+        rc = reset_next_id(c);
+        if (rc) return rc;
         rc = shard_launch_fused(c, P0, 0, 1, 1);
         if (rc) return rc;
         CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
@@ -1182,9 +1213,11 @@ extern "C" int gpm_shard_run(gpm_ctx* c, float* sweep_ms)
     if (world > 1 && !c->comm) return fail(GPM_E_STATE, "gpm_shard_run: neither an NCCL communicator nor peer regions are attached");
     {
         dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
-        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr);
+        k_init_planes<<<gr, b, 0, c->stream>>>(P0, c->seed, c->planes, nullptr, c->pid);
         c->launches++;
         CU(cudaGetLastError());
+        rc = reset_next_id(c);
+        if (rc) return rc;
         CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
         rc = shard_launch_stage(c, P0, 0, 0, nullptr, world, c->xchg);
         if (rc) return rc;
@@ -1227,7 +1260,8 @@ extern "C" int gpm_init_planes(gpm_ctx* c)
     int rc = build_kparams(c, true, P);
     if (rc) return rc;
     dim3 b(16, 16), gr((c->W + 15) / 16, (c->H + 15) / 16);
-    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr);
+    k_init_planes<<<gr, b, 0, c->stream>>>(P, c->seed, c->planes, c->rng_mode == GPM_RNG_STATEFUL ? c->rng : nullptr, c->pid);
+    { int rc_ = reset_next_id(c);  if (rc_) return rc_; }
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(c->prov, GPM_PROV_UNKNOWN, (size_t)c->W * c->H, c->stream));      // every plane is new: costs and memo are stale
@@ -1258,15 +1292,23 @@ extern "C" int gpm_measure_fetch_peak(gpm_ctx* c, double* gfetch_per_s)
     const int blocks = c->num_sms * 16, threads = 256, reps = 2048;
     const cudaTextureObject_t tex = c->color == 1 ? c->srcTex4 : c->srcTex;      // colour: three R32F channel planes per view
     const int layers = c->color == 1 ? 3 * c->V : c->V;
-    k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, c->W, c->H, layers, 64, sink);        // warm-up
-    CU(cudaEventRecord(c->ev0, c->stream));
-    k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, c->W, c->H, layers, reps, sink);
-    CU(cudaEventRecord(c->ev1, c->stream));
-    CU(cudaEventSynchronize(c->ev1));
-    CU(cudaGetLastError());
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    *gfetch_per_s = (double)blocks * threads * reps * 5.0 / (ms * 1e6);
+    int xmask = 1, ymask = 1;                      // random positions inside the image: the largest 2^k - 1 that fits
+    while (2 * xmask + 1 < c->W - 48) xmask = 2 * xmask + 1;
+    while (2 * ymask + 1 < c->H - 24) ymask = 2 * ymask + 1;
+    k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, xmask, ymask, layers, 64, sink);        // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, xmask, ymask, layers, reps, sink);
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaEventSynchronize(c->ev1));
+        CU(cudaGetLastError());
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const double g = (double)blocks * threads * reps * 5.0 / (ms * 1e6);
+        if (g > best) best = g;
+    }
+    *gfetch_per_s = best;
     return GPM_OK;
 }
 
@@ -1313,7 +1355,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
         if (slots != c->seen_slots) {
             CU(cudaStreamSynchronize(c->stream));
             cudaFree(c->seen);  c->seen = nullptr;
-            CU(cudaMalloc(&c->seen, (size_t)c->W * c->H * slots * sizeof(float4)));
+            CU(cudaMalloc(&c->seen, (size_t)c->W * c->H * slots * sizeof(unsigned)));
             c->seen_slots = slots;
         }
         CU(cudaMemsetAsync(c->memo_mask, 0, (size_t)c->W * c->H * sizeof(unsigned), c->stream));
@@ -1326,6 +1368,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "exchange") c->opt_exchange = value != 0;
     else if (n == "async_upload") c->opt_async_upload = value != 0;
     else if (n == "equal_rounds") c->opt_equal_rounds = value != 0;
+    else if (n == "fused_warps") c->opt_fused_warps = value;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");
     return GPM_OK;

@@ -103,9 +103,30 @@ __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
     return fl * sizeof(float);
 }
 
+// ---- exact memo of rejected work: plane identities ------------------------------------------------------------
+// Every plane carries a 32-bit identity: pid[p] = p + 1 at initialisation, a fresh number (atomic counter) whenever a
+// refinement creates a new plane, and COPIED when a plane propagates to a neighbour (gipuma.cu:867-871 copies the plane
+// verbatim).  Equal identity therefore implies bit-identical planes, so "this neighbour still holds the plane I was offered
+// before" is one 4-byte compare instead of a 16-byte one, the per-pixel memo shrinks from 8 x 16 + 16 to 8 x 4 + 4 bytes,
+// and a neighbour whose identity is remembered is skipped without even loading its plane.  (Planes that are equal by value
+// but were created independently have different identities: a skip is lost, never a decision.)
+struct Memo {
+    unsigned* pid;        // [H*W]       identity of the stored plane
+    unsigned* seen;       // [H*W*NC]    identity last offered to each pixel from each propagation direction
+    unsigned* refseen;    // [H*W]       identity of the plane from which the last all-rejected refinement started
+    unsigned* mask;       // [H*W]       validity bits of seen (0..19) and refseen (GPM_MEMO_REFINE)
+    unsigned* next_id;    // device counter of fresh identities
+};
+
 // ---- random plane initialisation — gipuma_init_cu2, gipuma.cu:996-1036 ----------------------
+__global__ void k_fill_ids(unsigned* __restrict__ pid, unsigned n)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pid[i] = i + 1u;
+}
+
 __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long long seed, float4* __restrict__ planes,
-                              unsigned* __restrict__ rng_state)
+                              unsigned* __restrict__ rng_state, unsigned* __restrict__ pid)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.W || y >= P.H) return;
@@ -132,6 +153,7 @@ __global__ void k_init_planes(const __grid_constant__ KParams P, unsigned long l
     const float depth = fmul(fmul(P.ref.f_cam, P.ref.baseline), frcp(disp));
     const float d = plane_d(P.ref, nx, ny, nz, px, py, depth);
     planes[(size_t)y * P.W + x] = make_float4(nx, ny, nz, d);
+    pid[(size_t)y * P.W + x] = (unsigned)(y * P.W + x) + 1u;
     if (rng_state) {
         unsigned* o = rng_state + ((size_t)y * P.W + x) * 6;
         o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
@@ -189,8 +211,7 @@ template <bool PACKED, bool COLOR, bool FUSED>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
         cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
-        unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, float4* __restrict__ seen,
-        float4* __restrict__ refseen, unsigned* __restrict__ memo_mask, int colour, int phase_mask,
+        unsigned* __restrict__ rng_state, unsigned char* __restrict__ prov, Memo M, int colour, int phase_mask,
         unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(128) float smem[];
@@ -233,11 +254,12 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
             constexpr unsigned NCMASK = (1u << NC) - 1u;
             float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
             bool mine_ok = false;
+            size_t mine_at = center;
             if (FUSED) {
                 if (lane < NC) {
                     mine_ok = (phase_mask & 1) && px >= kFusedGx0[lane] && px <= W - 1 - kFusedGx1[lane] &&
                               py >= kFusedGy0[lane] && py <= H - 1 - kFusedGy1[lane];
-                    if (mine_ok) mine = planes[(size_t)(py + kFusedDy[lane]) * W + (px + kFusedDx[lane])];
+                    mine_at = (size_t)(py + kFusedDy[lane]) * W + (px + kFusedDx[lane]);
                 }
             } else if (lane < 8) {
                 const int dist = lane < 4 ? 1 : 5;
@@ -250,8 +272,10 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                 else if (dir == 2) { ok = px > dist - 1;      qx = px - dist; }
                 else               { ok = px < W - dist;      qx = px + dist; }
                 mine_ok = ok && phase_on;
-                if (mine_ok) mine = planes[(size_t)qy * W + qx];
+                mine_at = (size_t)qy * W + qx;
             }
+            const unsigned mine_id = mine_ok ? M.pid[mine_at] : 0u;
+            unsigned own_id = M.pid[center];
             // Memo of rejected work.  A pixel's cost only ever decreases (gipuma.cu:867,986), and cost(p, plane) is a pure
             // function, so a neighbour plane this pixel has already been offered — accepted or not — can never be
             // accepted later: seen[p][k] holds the last plane offered from direction k; an unchanged neighbour is skipped
@@ -259,13 +283,11 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
             // the cost function of the fused kernel differs between its inlined call sites (P.site): the duplicate / memo
             // shortcuts below only pair candidates of sites with the same rounding variant
             const unsigned my_site = FUSED ? (unsigned)P.site[lane < NC ? lane : 0] : (COLOR ? 0u : 1u);
-            unsigned mmask = P.memo ? memo_mask[center] : 0u;
+            unsigned mmask = P.memo ? M.mask[center] : 0u;
             const bool old_ok = P.memo && lane < NC && ((mmask >> lane) & 1);
-            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (old_ok) old = seen[center * NC + lane];
-            const bool memo_hit = old_ok && mine_ok &&
-                                  __float_as_uint(old.x) == __float_as_uint(mine.x) && __float_as_uint(old.y) == __float_as_uint(mine.y) &&
-                                  __float_as_uint(old.z) == __float_as_uint(mine.z) && __float_as_uint(old.w) == __float_as_uint(mine.w);
+            const unsigned old_id = old_ok ? M.seen[center * NC + lane] : 0u;
+            const bool memo_hit = old_ok && mine_ok && old_id == mine_id;
+            if (mine_ok && !memo_hit) mine = planes[mine_at];          // a remembered neighbour is skipped below without its plane
             const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
             for (int k = 0; k < NC; k++) {
                 if (!((cand_mask >> k) & 1)) continue;
@@ -275,21 +297,17 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                 float4 nb;
                 nb.x = __shfl_sync(GPM_FULL, mine.x, k);  nb.y = __shfl_sync(GPM_FULL, mine.y, k);
                 nb.z = __shfl_sync(GPM_FULL, mine.z, k);  nb.w = __shfl_sync(GPM_FULL, mine.w, k);
+                const unsigned cand_id = __shfl_sync(GPM_FULL, mine_id, k);
                 // already offered to this pixel before, from ANY direction (the 8 memo entries double as a history)?
-                const bool known = old_ok && my_site == site && __float_as_uint(nb.x) == __float_as_uint(old.x) && __float_as_uint(nb.y) == __float_as_uint(old.y) &&
-                                   __float_as_uint(nb.z) == __float_as_uint(old.z) && __float_as_uint(nb.w) == __float_as_uint(old.w);
+                const bool known = old_ok && my_site == site && cand_id == old_id;
                 if (__any_sync(GPM_FULL, known)) { st.skip++; continue; }
                 // spatialPropagation_cu, gipuma.cu:832-874
                 const float disp_before = plane_depth(cam, nb.x, nb.y, nb.z, nb.w, fpx, fpy);
                 const bool in_range = disp_before >= cam.depthMin && disp_before <= cam.depthMax;   // :829-830, :865
                 // exact duplicates: cost(p, plane) is a pure function, so a plane equal to the current one or to an
                 // earlier candidate of this pixel cannot be accepted (`cost_before < *cost_now` is false)
-                const bool same_now = P.dedupe_self && prov_now == (int)site &&
-                                      __float_as_uint(nb.x) == __float_as_uint(norm_now.x) && __float_as_uint(nb.y) == __float_as_uint(norm_now.y) &&
-                                      __float_as_uint(nb.z) == __float_as_uint(norm_now.z) && __float_as_uint(nb.w) == __float_as_uint(norm_now.w);
-                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && my_site == site &&
-                                       __float_as_uint(nb.x) == __float_as_uint(mine.x) && __float_as_uint(nb.y) == __float_as_uint(mine.y) &&
-                                       __float_as_uint(nb.z) == __float_as_uint(mine.z) && __float_as_uint(nb.w) == __float_as_uint(mine.w);
+                const bool same_now = P.dedupe_self && prov_now == (int)site && cand_id == own_id;
+                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && my_site == site && cand_id == mine_id;
                 const bool dup = __any_sync(GPM_FULL, same_mine);
                 if (!in_range || same_now || dup) { st.skip++; continue; }
                 if (!window_ready) { setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
@@ -300,11 +318,12 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                     norm_now = nb;
                     cost_now = c;
                     prov_now = (int)site;
+                    own_id = cand_id;                                                            // a copy keeps its identity
                 }
             }
 
             if (P.memo && mine_ok && !memo_hit) {            // every candidate offered above is now known to this pixel
-                seen[center * NC + lane] = mine;
+                M.seen[center * NC + lane] = mine_id;
             }
             unsigned new_mask = mmask | (cand_mask & NCMASK);
             // The refinement candidates are a pure function of (pixel, plane at refinement start) in GPM_RNG_REFERENCE
@@ -312,16 +331,14 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
             // from exactly this plane before would reject them again.
             bool refine = (phase_mask & 4) != 0;
             if (refine && P.memo && P.rng_mode == 0 && (mmask & GPM_MEMO_REFINE)) {
-                const float4 old = refseen[center];
-                if (__float_as_uint(old.x) == __float_as_uint(norm_now.x) && __float_as_uint(old.y) == __float_as_uint(norm_now.y) &&
-                    __float_as_uint(old.z) == __float_as_uint(norm_now.z) && __float_as_uint(old.w) == __float_as_uint(norm_now.w)) {
+                if (M.refseen[center] == own_id) {
                     refine = false;
                     st.skip += 3;
                 }
             }
             if (refine) {
                 if (!window_ready) { setup_window<COLOR>(P, tile + P.tile_xo, ws, px, py, tile_x0, tile_y0, lane);  window_ready = true; }
-                const float4 norm_start = norm_now;
+                const unsigned id_start = own_id;
                 bool any_accept = false;
                 // planeRefinement_cu, gipuma.cu:928-994 with getRndDispAndUnitVector_cu, :890-927
                 Xorwow r = {0u, 0u, 0u, 0u, 0u, 0u};       // GPM_RNG_REFERENCE: gs.cs is never written (gipuma.cu:1840,1608)
@@ -366,16 +383,22 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                     unsigned* o = rng_state + center * 6;
                     o[0] = r.v0;  o[1] = r.v1;  o[2] = r.v2;  o[3] = r.v3;  o[4] = r.v4;  o[5] = r.d;
                 }
+                if (any_accept) {                                 // a new plane: one fresh identity for the pixel's final plane
+                    unsigned fresh = 0u;
+                    if (lane == 0) fresh = atomicAdd(M.next_id, 1u);
+                    own_id = __shfl_sync(GPM_FULL, fresh, 0);
+                }
                 if (P.memo && P.rng_mode == 0) {
-                    if (!any_accept) { if (lane == 0) refseen[center] = norm_start;  new_mask |= GPM_MEMO_REFINE; }
+                    if (!any_accept) { if (lane == 0) M.refseen[center] = id_start;  new_mask |= GPM_MEMO_REFINE; }
                     else new_mask &= ~GPM_MEMO_REFINE;
                 }
             }
-            if (P.memo && lane == 0 && new_mask != mmask) memo_mask[center] = new_mask;
+            if (P.memo && lane == 0 && new_mask != mmask) M.mask[center] = new_mask;
             if (lane == 0) {                                                                     // :1585-1587
                 cost[center] = cost_now;
                 planes[center] = norm_now;
                 prov[center] = (unsigned char)prov_now;
+                M.pid[center] = own_id;
             }
         }
         if (lane == 0) idx = (int)blockIdx.z * per_slice + atomicAdd(counter, 1);
@@ -486,10 +509,10 @@ __device__ __forceinline__ float4 shard_refine_candidate(const KParams& P, const
 // Accept of stage `stage` at pixel (px, py) from the exchanged lists (one warp; every lane returns the same state).
 // stage 1: the 8 propagation slots in the reference's order (gipuma.cu:1571-1582, 1450-1462; accept rule :867-871);
 // stage >= 2: one refinement step (:986-990).
-__device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float4* __restrict__ planes, const ShardState& S,
+__device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float4* __restrict__ planes, const ShardState& S, const Memo& M,
                                                    int px, int py, int stage, const float* __restrict__ gathered, int world, size_t rank_stride,
                                                    float4& norm_now, float& cost_now, float& disp_now, int& prov_now, unsigned& sf,
-                                                   unsigned lane)
+                                                   unsigned& own_id, unsigned lane)
 {
     const int W = P.W, H = P.H, Wh = (W + 1) >> 1, nb = P.n_best;
     const size_t center = (size_t)py * W + px;
@@ -509,6 +532,7 @@ __device__ __forceinline__ void shard_accept_pixel(const KParams& P, const float
                 const int dist = k < 4 ? 1 : 5, dir = k & 3;
                 const int qx = px + (dir == 2 ? -dist : dir == 3 ? dist : 0), qy = py + (dir == 0 ? -dist : dir == 1 ? dist : 0);
                 norm_now = planes[(size_t)qy * W + qx];                 // other colour: not written during this colour's stages
+                own_id = M.pid[(size_t)qy * W + qx];                    // a copy keeps its identity
                 disp_now = plane_depth(P.ref, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
                 cost_now = c;
                 prov_now = P.color ? 0 : 1;
@@ -528,8 +552,7 @@ template <bool PACKED, bool COLOR>
 __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float* __restrict__ sCam, const float* __restrict__ tile,
                                                   const WarpScratch& ws, cudaTextureObject_t src, cudaTextureObject_t grad,
                                                   float4* __restrict__ planes, float* __restrict__ cost, unsigned char* __restrict__ prov,
-                                                  const ShardState& S, float4* __restrict__ seen, float4* __restrict__ refseen,
-                                                  unsigned* __restrict__ memo_mask, int px, int py, int tile_x0, int tile_y0,
+                                                  const ShardState& S, const Memo& M, int px, int py, int tile_x0, int tile_y0,
                                                   int stage, int last_stage, const float* __restrict__ gathered_prev, int world,
                                                   float* __restrict__ xchg, unsigned lane, WarpStats& st,
                                                   size_t rank_stride = 0, const ShardP2P* X = nullptr, size_t slot_off = 0)
@@ -565,25 +588,32 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
     int prov_now = prov[center];
     unsigned sf = stage >= 2 ? (unsigned)S.sflags[center] : 0u;
     float disp_now = stage >= 2 ? S.dispbuf[center] : plane_depth(cam, norm_now.x, norm_now.y, norm_now.z, norm_now.w, fpx, fpy);
-    unsigned mmask = P.memo ? memo_mask[center] : 0u;
+    unsigned mmask = P.memo ? M.mask[center] : 0u;
     unsigned new_mask = mmask;
+    unsigned own_id = M.pid[center];
     if (stage >= 2) {
-        shard_accept_pixel(P, planes, S, px, py, stage - 1, gathered_prev, world, rank_stride, norm_now, cost_now, disp_now, prov_now, sf, lane);
+        shard_accept_pixel(P, planes, S, M, px, py, stage - 1, gathered_prev, world, rank_stride, norm_now, cost_now, disp_now, prov_now, sf, own_id, lane);
         if (stage == 2) {
             // refinement memo (see k_sweep): the S candidates are a pure function of (pixel, plane at refinement start)
             sf = 0u;
             if (P.memo && P.rng_mode == 0) {
-                if ((mmask & GPM_MEMO_REFINE) && same_bits(refseen[center], norm_now)) sf = GPM_SF_SKIP_REFINE;
-                else { if (lane == 0) refseen[center] = norm_now;  new_mask &= ~GPM_MEMO_REFINE; }
+                if ((mmask & GPM_MEMO_REFINE) && M.refseen[center] == own_id) sf = GPM_SF_SKIP_REFINE;
+                else { if (lane == 0) M.refseen[center] = own_id;  new_mask &= ~GPM_MEMO_REFINE; }
             }
         }
     }
     float* out = xchg + ((size_t)py * Wh + (px >> 1)) * ((stage == 1 || rank_stride) ? 8 : 1) * nb;      // see shard_accept_pixel
     if (stage > last_stage) {                               // closing pass of a colour: only the accept of the last refinement step
         if (P.memo && P.rng_mode == 0 && !(sf & (GPM_SF_SKIP_REFINE | GPM_SF_ACCEPTED))) new_mask |= GPM_MEMO_REFINE;
+        if (sf & GPM_SF_ACCEPTED) {                         // the refinement created a new plane: one fresh identity
+            unsigned fresh = 0u;
+            if (lane == 0) fresh = atomicAdd(M.next_id, 1u);
+            own_id = __shfl_sync(GPM_FULL, fresh, 0);
+        }
     } else if (stage == 1) {
         float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
         bool mine_ok = false;
+        size_t mine_at = center;
         if (lane < 8) {
             const int dist = lane < 4 ? 1 : 5, dir = lane & 3;
             int qx = px, qy = py;
@@ -593,12 +623,13 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
             else if (dir == 2) { ok = px > dist - 1;  qx = px - dist; }
             else               { ok = px < W - dist;  qx = px + dist; }
             mine_ok = ok;
-            if (mine_ok) mine = planes[(size_t)qy * W + qx];
+            mine_at = (size_t)qy * W + qx;
         }
+        const unsigned mine_id = mine_ok ? M.pid[mine_at] : 0u;
         const bool old_ok = P.memo && lane < 8 && ((mmask >> lane) & 1);
-        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (old_ok) old = seen[center * 8 + lane];
-        const bool memo_hit = old_ok && mine_ok && same_bits(old, mine);
+        const unsigned old_id = old_ok ? M.seen[center * 8 + lane] : 0u;
+        const bool memo_hit = old_ok && mine_ok && old_id == mine_id;
+        if (mine_ok && !memo_hit) mine = planes[mine_at];
         const unsigned cand_mask = __ballot_sync(GPM_FULL, mine_ok);
         const int site = COLOR ? 0 : 1;
         bool window_ready = false;
@@ -606,15 +637,16 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
             float4 nbp;
             nbp.x = __shfl_sync(GPM_FULL, mine.x, k);  nbp.y = __shfl_sync(GPM_FULL, mine.y, k);
             nbp.z = __shfl_sync(GPM_FULL, mine.z, k);  nbp.w = __shfl_sync(GPM_FULL, mine.w, k);
+            const unsigned cand_id = __shfl_sync(GPM_FULL, mine_id, k);
             bool skip = !((cand_mask >> k) & 1);
-            if (!skip) skip = __any_sync(GPM_FULL, old_ok && same_bits(nbp, old));          // offered before, from any direction
+            if (!skip) skip = __any_sync(GPM_FULL, old_ok && cand_id == old_id);            // offered before, from any direction
             if (!skip) {
                 const float d = plane_depth(cam, nbp.x, nbp.y, nbp.z, nbp.w, fpx, fpy);
                 const bool in_range = d >= cam.depthMin && d <= cam.depthMax;
                 // a plane equal to the current one (cost of the same rounding variant) or to an earlier slot can never pass
                 // `cost < cost_now`: cost_now only decreases while the slots are accepted in order
-                const bool same_now = P.dedupe_self && prov_now == site && same_bits(nbp, norm_now);
-                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && same_bits(nbp, mine);
+                const bool same_now = P.dedupe_self && prov_now == site && cand_id == own_id;
+                const bool same_mine = P.dedupe_cand && mine_ok && (int)lane < k && cand_id == mine_id;
                 skip = !in_range || same_now || __any_sync(GPM_FULL, same_mine);
             }
             if (skip) { st.skip++;  if ((int)lane < nb) out[k * nb + lane] = inf;  __syncwarp();  continue; }
@@ -622,7 +654,7 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
             eval_plane<(COLOR ? 0 : 1), PACKED, COLOR>(P, sCam, ws, src, grad, nbp.x, nbp.y, nbp.z, nbp.w, inf, lane, st, &c0, &c1);
             local_topn(P, c0, c1, lane, out + k * nb);
         }
-        if (P.memo && mine_ok && !memo_hit) seen[center * 8 + lane] = mine;
+        if (P.memo && mine_ok && !memo_hit) M.seen[center * 8 + lane] = mine_id;
         new_mask |= (cand_mask & 0xffu);
         publish(out, 8 * nb);
     } else {
@@ -640,9 +672,9 @@ __device__ __forceinline__ void shard_stage_pixel(const KParams& P, const float*
         publish(out, nb);
     }
     if (lane == 0) {
-        if (stage >= 2) { planes[center] = norm_now;  cost[center] = cost_now;  prov[center] = (unsigned char)prov_now; }
+        if (stage >= 2) { planes[center] = norm_now;  cost[center] = cost_now;  prov[center] = (unsigned char)prov_now;  M.pid[center] = own_id; }
         if (stage >= 1) { S.dispbuf[center] = disp_now;  S.sflags[center] = (unsigned char)sf; }
-        if (P.memo && new_mask != mmask) memo_mask[center] = new_mask;
+        if (P.memo && new_mask != mmask) M.mask[center] = new_mask;
     }
 }
 
@@ -652,8 +684,7 @@ template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_stage(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams, const float* __restrict__ refpad,
               cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes, float* __restrict__ cost,
-              unsigned char* __restrict__ prov, ShardState S, float4* __restrict__ seen, float4* __restrict__ refseen,
-              unsigned* __restrict__ memo_mask, int colour, int stage, int last_stage, const float* __restrict__ gathered_prev,
+              unsigned char* __restrict__ prov, ShardState S, Memo M, int colour, int stage, int last_stage, const float* __restrict__ gathered_prev,
               int world, float* __restrict__ xchg, unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(128) float smem[];
@@ -675,7 +706,7 @@ k_shard_stage(const __grid_constant__ KParams P, const __grid_constant__ CUtenso
         if (stage == 0) { px = blockIdx.x * GPM_TILE + (idx & 31);  py = blockIdx.y * GPM_TILE + (idx >> 5); }
         else { const int tx = idx & 31, ty = idx >> 5;  px = blockIdx.x * GPM_TILE + tx;  py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1); }
         if (px >= P.W || py >= P.H) continue;
-        shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, seen, refseen, memo_mask, px, py,
+        shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, M, px, py,
                                          tile_x0, tile_y0, stage, last_stage, gathered_prev, world, xchg, lane, st);
     }
     flush_stats(stats, st, lane);
@@ -726,8 +757,7 @@ template <bool PACKED, bool COLOR>
 __global__ void __launch_bounds__(GPM_LB_THREADS, GPM_LB_BLOCKS)
 k_shard_fused(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap tmap, const ViewCam* __restrict__ cams,
               const float* __restrict__ refpad, cudaTextureObject_t src, cudaTextureObject_t grad, float4* __restrict__ planes,
-              float* __restrict__ cost, unsigned char* __restrict__ prov, ShardState S, float4* __restrict__ seen,
-              float4* __restrict__ refseen, unsigned* __restrict__ memo_mask, int colour, int init_phase, int last_stage,
+              float* __restrict__ cost, unsigned char* __restrict__ prov, ShardState S, Memo M, int colour, int init_phase, int last_stage,
               const __grid_constant__ ShardP2P X, unsigned seq0, unsigned long long* __restrict__ stats)
 {
     extern __shared__ __align__(128) float smem[];
@@ -766,7 +796,7 @@ k_shard_fused(const __grid_constant__ KParams P, const __grid_constant__ CUtenso
                 }
                 continue;
             }
-            shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, seen, refseen, memo_mask, px, py,
+            shard_stage_pixel<PACKED, COLOR>(P, sCam, tile, ws, src, grad, planes, cost, prov, S, M, px, py,
                                              tile_x0, tile_y0, stage, lastS, prev, X.world, outb, lane, st, slot, &X, slot_off);
         }
         if (!closing) p2p_signal(X, bid, seq);
@@ -808,20 +838,21 @@ __global__ void k_finalize(const __grid_constant__ KParams P, float4* __restrict
     planes[center] = o;
 }
 
-// Ceiling of the unit that bounds this path, measured in process: filtered R32F fetches per second of the texture unit for
-// dense footprints (32 lanes = 8 x 4 adjacent texels, the best case of tools/texbench.cu) on the context's own layered
-// texture.  bench.py divides the fetch rate it achieves by this number (roofline.binding_unit).
-__global__ void k_fetch_peak(cudaTextureObject_t src, int W, int H, int V, int reps, float* __restrict__ sink)
+// Ceiling of the unit that bounds this path, measured in process: filtered R32F fetches per second of the texture unit in its
+// best case — 32 lanes = 16 x 2 adjacent texels (every hardware quad a 2x2 block; 1143 Gfetch/s in tools/texbench.cu), the five
+// taps of the reference's sample pattern, one layer per warp — on the context's own layered texture.  bench.py divides the
+// fetch rate it achieves by this number (roofline.binding_unit).
+__global__ void k_fetch_peak(cudaTextureObject_t src, int xmask, int ymask, int V, int reps, float* __restrict__ sink)
 {
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const float dx = (float)(lane & 7), dy = (float)(lane >> 3);
+    const float dx = (float)(lane >> 1), dy = (float)(lane & 1);
+    const int v = warp % V;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
     unsigned h = (unsigned)warp * 2654435761u + 12345u;
     for (int r = 0; r < reps; r++) {
         h = h * 1664525u + 1013904223u;
-        const float x = 8.0f + (float)((h >> 8) % (unsigned)(W - 32)) + 0.37f + dx;
-        const float y = 8.0f + (float)((h >> 4) % (unsigned)(H - 24)) + 0.61f + dy;
-        const int v = (int)((h >> 28) % (unsigned)V);
+        const float x = 8.37f + (float)((h >> 8) & (unsigned)xmask) + dx;
+        const float y = 8.61f + (float)((h >> 20) & (unsigned)ymask) + dy;
         a0 += tex2DLayered<float>(src, x, y, v);
         a1 += tex2DLayered<float>(src, x + 1.0f, y, v);
         a2 += tex2DLayered<float>(src, x - 1.0f, y, v);

@@ -186,6 +186,8 @@ int gpm_debug_packed_mismatches(gpm_ctx* ctx, unsigned* count, float* records512
  * "shard_async" (0): 1 makes gpm_shard_stage / gpm_shard_finish_init return after enqueueing on gpm_stream() — run the
  * collective on that stream (or order it with events) instead of paying a host synchronisation per stage;
  * "tma" (1): stage the reference window with one cp.async.bulk.tensor (TMA) per block instead of a cooperative copy;
+ * "fused_warps" (8): warps per block of the fused shard kernel (8 = two resident blocks per SM: one samples while the other
+ * waits for its peers' lists; 16 = one);
  * "exchange" (1): view shard over peer memory when regions are attached, 0 = NCCL all-gather per stage;
  * "async_upload" (0): 1 lets gpm_set_reference / gpm_set_view return without a host synchronisation — the caller keeps its
  * (page-locked) image buffers unchanged until the next gpm_run / gpm_sweep returns;
