@@ -15,7 +15,8 @@ occluding blocks, a texture-less band and sensor noise):
                            parameters) whose source views are sharded over the N ranks; after every exchange stage the ranks'
                            local top-n_best view costs are all-gathered over NCCL/NVLink (gpm_shard_run, behind the C-ABI)
                            and combined exactly as pmCostMultiview_cu does (gipuma.cu:742-806).  "scaling": "strong".
-                           Default exchange: fused into the stage kernels over peer memory (NVLink); --exchange nccl: all-gather.
+                           Default exchange: one ncclAllGather per stage (measured 4-6 % faster than the fused peer-memory
+                           kernel); --exchange p2p selects the fused kernel.
                            Rank 0 also runs the same job unsharded and reports whether the outputs are bit-identical.
   --mode batch             every rank its own reference view (scripts/dtu_fast.sh:30-55), no collective, weak scaling.
   --mode hybrid --shard G  BASELINE configs[4]: N/G groups, each one 3200x2400 / 64-view reference view sharded G ways.
@@ -138,7 +139,7 @@ def config_dict(args, mode, config, shard, world, sc_name, W, H, V, iters, box, 
         suffix += ", hard scene (occluders, texture-less band, sensor noise)"
     par = {"single": "one reference view on one GPU",
            "batch": "reference-view batch: one independent reference view per GPU, no collective",
-           "view_shard": "one reference view, source views sharded over the GPUs; per exchange stage every rank's local top-n_best view costs reach all ranks (fused peer-memory exchange over NVLink, or NCCL all-gather with --exchange nccl)",
+           "view_shard": "one reference view, source views sharded over the GPUs; per exchange stage every rank's local top-n_best view costs reach all ranks (NCCL all-gather over NVLink behind the C-ABI; --exchange p2p: fused peer-memory exchange)",
            "hybrid": "groups of %d GPUs shard the source views of their group's reference view; groups are independent" % shard}[mode]
     return {"workload": "%s: %s, %dx%d, %d source views, %d iterations, blocksize %d, n_best %d" % (config_label(config), sc_name, W, H, V, iters, box, n_best) + suffix,
             "mode": mode, "parallelism": par,
@@ -534,7 +535,8 @@ def main():
     ap.add_argument("--config", type=int, default=0, help="1-5: BASELINE.json configs; 6: 1600x1200 / 60 views (default of view_shard)")
     ap.add_argument("--shard", type=int, default=0, help="hybrid: GPUs per reference view")
     ap.add_argument("--scene", default="smooth", choices=["smooth", "hard"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="sharded modes: fused peer-memory exchange or NCCL all-gather per stage")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="sharded modes: one ncclAllGather per exchange stage (default: measured fastest) or the fused peer-memory exchange")
     ap.add_argument("--no-check", action="store_true", help="sharded modes: skip the unsharded comparison run on rank 0")
     ap.add_argument("--color", action="store_true", help="float4 images (the reference's -color_processing)")
     ap.add_argument("--neighbours", type=int, default=8, choices=[8, 20],

@@ -14,6 +14,7 @@
 #include "../../include/gipuma_b200.h"
 #include "gpm_kernels.cuh"
 
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -69,7 +70,7 @@ struct gpm_ctx {
     unsigned p2p_seq = 0;
     int opt_exchange = 1;
     int opt_equal_rounds = 0;
-    int opt_fused_warps = 8;                     // warps per block of k_shard_fused: 8 -> two blocks per SM, one samples while the other waits for its peers
+    int opt_fused_warps = 16;                    // warps per block of k_shard_fused: 8 -> two blocks per SM (one samples while the other waits); measured no faster
     int opt_async_upload = 0;                    // 1: image uploads return without a host synchronisation (caller keeps its buffers alive until the next run)
     bool inputs_dirty = false;                   // an input changed: stored costs / memo are stale (cleared once, at the next launch)                        // 1: peer-memory exchange when attached; 0: NCCL all-gather per stage
     unsigned* seen = nullptr;        // [H*W*ncand] identity of the plane last offered to each pixel from each of the 8 (fused kernel: 20) propagation directions
@@ -1292,9 +1293,11 @@ extern "C" int gpm_measure_fetch_peak(gpm_ctx* c, double* gfetch_per_s)
     const int blocks = c->num_sms * 16, threads = 256, reps = 2048;
     const cudaTextureObject_t tex = c->color == 1 ? c->srcTex4 : c->srcTex;      // colour: three R32F channel planes per view
     const int layers = c->color == 1 ? 3 * c->V : c->V;
-    int xmask = 1, ymask = 1;                      // random positions inside the image: the largest 2^k - 1 that fits
-    while (2 * xmask + 1 < c->W - 48) xmask = 2 * xmask + 1;
-    while (2 * ymask + 1 < c->H - 24) ymask = 2 * ymask + 1;
+    // random positions inside a window of at most 512 x 512 texels of at most 4 layers: the UNIT's ceiling is wanted, so the
+    // working set must stay in L2 whatever the image size (a 3200 x 2400 x 64-layer array would make this a DRAM test)
+    int xmask = 1, ymask = 1;
+    while (2 * xmask + 1 < c->W - 48 && xmask < 511) xmask = 2 * xmask + 1;
+    while (2 * ymask + 1 < c->H - 24 && ymask < 511) ymask = 2 * ymask + 1;
     k_fetch_peak<<<blocks, threads, 0, c->stream>>>(tex, xmask, ymask, layers, 64, sink);        // warm-up
     double best = 0.0;
     for (int rep = 0; rep < 3; rep++) {

@@ -713,12 +713,17 @@ k_shard_stage(const __grid_constant__ KParams P, const __grid_constant__ CUtenso
 }
 
 // ---- fused compute + exchange over peer memory (NVLink / NVSwitch) ---------------------------------------------------
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+// Polling load: relaxed, system scope (served by L2, the point of coherence for peer stores into this GPU's memory).  The
+// acquire is ONE fence after the poll succeeds: an acquiring load (or a system-scope fence) invalidates the SM's whole L1 —
+// the texture cache of every resident block — so it must not sit inside the spin loop (measured: with ld.acquire.sys in the
+// loop two resident blocks per SM ran 7 % SLOWER than one, profiles/r02_shard_*_4gpu.json).
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p)
 {
     unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -729,11 +734,12 @@ __device__ __forceinline__ void p2p_wait(const ShardP2P& X, unsigned bid, unsign
     if ((int)threadIdx.x < X.world && (int)threadIdx.x != X.me) {
         const unsigned* f = X.flags[X.me] + (size_t)threadIdx.x * X.nblocks + bid;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - seq) < 0) {
+        while ((int)(ld_relaxed_sys(f) - seq) < 0) {
             if (*(volatile unsigned*)X.err) break;
             if (clock64() - t0 > (1LL << 33)) { atomicExch(X.err, 1u);  break; }      // ~4 s: fail loudly on the host, never hang
-            __nanosleep(100);
+            __nanosleep(200);
         }
+        fence_acquire_sys();
     }
     __syncthreads();
 }

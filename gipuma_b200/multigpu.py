@@ -104,7 +104,7 @@ def hybrid_layout(world: int, shard: int):
 
 
 def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank: int, world: int, shard: int,
-               device: int = 0, on_result: Optional[Callable] = None, exchange: str = "p2p") -> List[float]:
+               device: int = 0, on_result: Optional[Callable] = None, exchange: str = "nccl") -> List[float]:
     """Reference views are dealt round-robin to world/shard groups; inside a group the source views are sharded and
     combined with one all-gather per stage over the group's own communicator.  Returns wall seconds per reference view."""
     import time
@@ -134,12 +134,12 @@ def run_hybrid(make_scene: Callable[[int], object], n_reference_views: int, rank
 
 class ViewShardRunner:
     """One reference view, source views sharded over `world` ranks.  All device work runs behind the C-ABI
-    (gpm_shard_run): with exchange="p2p" (default) one fused kernel per colour pass that stores the lists into the peers'
-    memory over NVLink as it samples; with exchange="nccl" one stage kernel + ncclAllGather per exchange stage.
+    (gpm_shard_run): with exchange="nccl" (default, measured fastest) one stage kernel + ncclAllGather per exchange stage;
+    with exchange="p2p" one fused kernel per colour pass that stores the lists into the peers' memory over NVLink as it samples.
     torch.distributed is only used at set-up, to pass the NCCL unique id and the CUDA IPC handles around."""
 
     def __init__(self, scene, rank: int, world: int, device: int = 0, seed: int = 0xC0FFEE, group=None, options=None,
-                 exchange: str = "p2p"):
+                 exchange: str = "nccl"):
         from . import api
         self.scene, self.rank, self.world, self.group = scene, rank, world, group
         self.local = partition_views(scene.n_views, world)[rank]

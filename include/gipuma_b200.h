@@ -151,7 +151,7 @@ int gpm_shard_unique_id(void* id128);
 int gpm_shard_comm_init(gpm_ctx* ctx, const void* id128, int rank, int world);
 int gpm_shard_comm_attach(gpm_ctx* ctx, void* nccl_comm, int rank, int world);
 int gpm_shard_run(gpm_ctx* ctx, float* sweep_ms);
-/* Fused compute + exchange over peer memory (NVLink / NVSwitch), the default of gpm_shard_run once attached: every rank
+/* Fused compute + exchange over peer memory (NVLink / NVSwitch), what gpm_shard_run uses once regions are attached: every rank
  * exports one exchange region (CUDA IPC handle, 64 bytes; `local_ptr` for ranks of the same process), the handles of all
  * ranks are handed to gpm_shard_p2p_attach, and from then on one kernel per colour pass stores each pixel's lists directly
  * into the peers' regions while it samples and synchronises tile by tile with arrival flags — no collective launches.
@@ -186,8 +186,8 @@ int gpm_debug_packed_mismatches(gpm_ctx* ctx, unsigned* count, float* records512
  * "shard_async" (0): 1 makes gpm_shard_stage / gpm_shard_finish_init return after enqueueing on gpm_stream() — run the
  * collective on that stream (or order it with events) instead of paying a host synchronisation per stage;
  * "tma" (1): stage the reference window with one cp.async.bulk.tensor (TMA) per block instead of a cooperative copy;
- * "fused_warps" (8): warps per block of the fused shard kernel (8 = two resident blocks per SM: one samples while the other
- * waits for its peers' lists; 16 = one);
+ * "fused_warps" (16): warps per block of the fused shard kernel (8 = two resident blocks per SM: one samples while the other
+ * waits for its peers' lists — measured no faster);
  * "exchange" (1): view shard over peer memory when regions are attached, 0 = NCCL all-gather per stage;
  * "async_upload" (0): 1 lets gpm_set_reference / gpm_set_view return without a host synchronisation — the caller keeps its
  * (page-locked) image buffers unchanged until the next gpm_run / gpm_sweep returns;

@@ -16,7 +16,7 @@ ap.add_argument("--views", type=int, default=None)
 ap.add_argument("--iters", type=int, default=None)
 ap.add_argument("--hybrid", type=int, default=0, help="view-shard width; world/width groups take different reference views")
 ap.add_argument("--refs", type=int, default=2)
-ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="fused peer-memory exchange or one ncclAllGather per stage")
+ap.add_argument("--exchange", default="nccl", choices=["p2p", "nccl"], help="fused peer-memory exchange or one ncclAllGather per stage")
 ap.add_argument("--repeat", type=int, default=2)
 ap.add_argument("--opt", nargs="*", default=[], help="gpm_set_option name=value pairs for the sharded contexts")
 args = ap.parse_args()
@@ -43,7 +43,8 @@ if args.hybrid:
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     sys.exit(0)
-sc = S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters)
+sc = S.make_config(args.config, rows=args.rows, cols=args.cols, n_views=args.views, iterations=args.iters,
+                   workers=max(1, min(32, len(os.sched_getaffinity(0)) // max(1, world))))
 opts = {k: int(v) for k, v in (o.split("=") for o in args.opt)}
 run = M.ViewShardRunner(sc, rank, world, device=local, exchange=args.exchange, options=opts)
 run.run()                                              # warm-up (NCCL communicator, kernels)
