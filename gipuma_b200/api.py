@@ -149,16 +149,31 @@ def pack_camera(c) -> GpmCamera:
 
 
 def _ptr(a):
-    """void* of a numpy array, a torch tensor (host or CUDA) or a raw integer address."""
+    """void* of a numpy array, a torch tensor (host or CUDA) or a raw integer address.  The C-ABI reads / writes float32
+    row-major memory: anything else is refused here instead of being reinterpreted silently."""
     if a is None:
         return None, 0
     if isinstance(a, int):
         return C.c_void_p(a), 1
     if isinstance(a, np.ndarray):
+        if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError("numpy buffers must be C-contiguous float32 (got %s, contiguous=%s)" % (a.dtype, a.flags["C_CONTIGUOUS"]))
         return C.c_void_p(a.ctypes.data), 0
     if hasattr(a, "data_ptr"):
+        import torch
+        if a.dtype != torch.float32 or not a.is_contiguous():
+            raise TypeError("torch buffers must be contiguous float32 (got %s)" % (a.dtype,))
+        if a.is_cuda:
+            torch.cuda.current_stream(a.device).synchronize()      # the context works on its own stream: the producer must be done
         return C.c_void_p(a.data_ptr()), 1 if a.is_cuda else 0
     raise TypeError("unsupported buffer type %r" % type(a))
+
+
+def _image(a):
+    """Images may come as any real numpy dtype: converted to contiguous float32 here (what main.cpp's loaders produce)."""
+    if isinstance(a, np.ndarray) and (a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]):
+        return np.ascontiguousarray(a, dtype=np.float32)
+    return a
 
 
 class Context:
@@ -204,12 +219,14 @@ class Context:
         return len(shape) == 3 and shape[-1] == 4
 
     def set_reference(self, img, cam, pitch_bytes: int = 0):
+        img = _image(img)
         ptr, dev = _ptr(img)
         g = pack_camera(cam)
         fn = self.lib.gpm_set_reference_color if self._is_color(img) else self.lib.gpm_set_reference
         self._check(fn(self.h, ptr, pitch_bytes, dev, C.byref(g)))
 
     def set_view(self, v: int, img, cam, pitch_bytes: int = 0):
+        img = _image(img)
         ptr, dev = _ptr(img)
         g = pack_camera(cam)
         fn = self.lib.gpm_set_view_color if self._is_color(img) else self.lib.gpm_set_view

@@ -79,3 +79,36 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "gipuma_oracle" not in txt, f
+
+
+def test_python_binding_refuses_buffers_it_would_reinterpret():
+    """api._ptr hands raw addresses to the C-ABI, which reads float32 row-major memory: other dtypes / strided views are refused
+    (images are converted, outputs must be right)."""
+    import numpy as np
+    from gipuma_b200 import api
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros((4, 4), np.float64))
+    with pytest.raises(TypeError):
+        api._ptr(np.zeros((4, 8), np.float32)[:, ::2])
+    img = api._image(np.arange(12, dtype=np.uint8).reshape(3, 4))
+    assert img.dtype == np.float32 and img.flags["C_CONTIGUOUS"] and img[2, 3] == 11.0
+
+
+def test_bench_arms_describe_the_same_workload():
+    """The driver compares the two arms' `config` objects: they must be identical for every mode (same_config)."""
+    import argparse
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world, mode in ((1, "auto"), (2, "auto"), (8, "auto"), (4, "batch"), (8, "hybrid")):
+        args = argparse.Namespace(mode=mode, config=0, shard=0, color=False, neighbours=8, scene="smooth")
+        m, cfg, shard = bench.resolve(args, world)
+        a = bench.config_dict(args, m, cfg, shard, world, "scene", 1600, 1200, 60, 8, 15, 3)
+        b = bench.config_dict(args, m, cfg, shard, world, "scene", 1600, 1200, 60, 8, 15, 3)
+        assert a == b and a["mode"] == m
+        if world == 1:
+            assert m == "single" and cfg == 2
+        if mode == "auto" and world > 1:
+            assert m == "view_shard" and cfg == 6 and shard == world
