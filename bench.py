@@ -171,7 +171,7 @@ def load_traffic(key):
 
 def cpu_baseline(sc, neighbours: int = 8) -> dict:
     """Single-thread C restatement on a fixed band: one iteration over rows [H/2, H/2 + 8) of the workload; then the same
-    code with every host thread on rows [H/2, H/2 + 4 * threads) (reported separately)."""
+    code with every host thread on rows [H/2, H/2 + 2 * threads) (reported separately)."""
     from oracle import pyoracle
     o = pyoracle.Oracle(sc)
     rng = np.random.default_rng(0)
@@ -200,8 +200,8 @@ def cpu_baseline(sc, neighbours: int = 8) -> dict:
            "sample": "1 iteration over the fixed rows [%d,%d) of the same %dx%d / %d-view workload, 1 thread: %.1f s (host has %d cores)"
                      % (y0, y0 + 8, W, H, sc.n_views, dt1, os.cpu_count() or 0)}
     if all_threads > 1:
-        vm, dtm, n, _ = band(min(H // 2, 4 * all_threads), all_threads)
-        out["all_threads"] = {"value": vm, "cores": n, "sample": "rows [%d,%d), %.1f s" % (y0, y0 + min(H // 2, 4 * all_threads), dtm)}
+        vm, dtm, n, _ = band(min(H // 2, 2 * all_threads), all_threads)
+        out["all_threads"] = {"value": vm, "cores": n, "sample": "rows [%d,%d), %.1f s" % (y0, y0 + min(H // 2, 2 * all_threads), dtm)}
     return out
 
 
@@ -303,7 +303,7 @@ def run_ours_single_or_batch(args, mode, config, rank, world, local, sc):
     if rank == 0:
         fetch_peak = ctx.measure_fetch_peak()
         ablation = {}
-        if world == 1:                       # how much of the speed is skipped work: the same job without the exact shortcuts
+        if world == 1 and not args.no_ablation:   # how much of the speed is skipped work: the same job without the exact shortcuts
             for name, opts in (("value_memo_off", {"memo": 0}), ("value_prune_off", {"prune": 0}),
                                ("value_memo_prune_dedupe_off", {"memo": 0, "prune": 0, "dedupe": 0}), ("value_quadperm_off", {"quadperm": 0})):
                 for k, v in opts.items():
@@ -537,6 +537,7 @@ def main():
     ap.add_argument("--scene", default="smooth", choices=["smooth", "hard"])
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="sharded modes: one ncclAllGather per exchange stage (default: measured fastest) or the fused peer-memory exchange")
+    ap.add_argument("--no-ablation", action="store_true", help="N = 1: skip the extra runs without memo / lower bound / lane order")
     ap.add_argument("--no-check", action="store_true", help="sharded modes: skip the unsharded comparison run on rank 0")
     ap.add_argument("--color", action="store_true", help="float4 images (the reference's -color_processing)")
     ap.add_argument("--neighbours", type=int, default=8, choices=[8, 20],
