@@ -24,6 +24,10 @@
 
 using namespace gpm;
 
+#ifndef GPM_PREPASS_DEFAULT
+#define GPM_PREPASS_DEFAULT 0
+#endif
+
 static thread_local std::string g_err;
 
 static int fail(int code, const std::string& msg)
@@ -70,6 +74,7 @@ struct gpm_ctx {
     unsigned p2p_seq = 0;
     int opt_exchange = 1;
     int opt_equal_rounds = 0;
+    int opt_prepass = GPM_PREPASS_DEFAULT;       // k_sweep's thread-per-pixel pre-pass over idle pixels (env GPM_PREPASS overrides at gpm_create)
     int opt_fused_warps = 16;                    // warps per block of k_shard_fused: 8 -> two blocks per SM (one samples while the other waits); measured no faster
     int opt_async_upload = 0;                    // 1: image uploads return without a host synchronisation (caller keeps its buffers alive until the next run)
     bool inputs_dirty = false;                   // an input changed: stored costs / memo are stale (cleared once, at the next launch)                        // 1: peer-memory exchange when attached; 0: NCCL all-gather per stage
@@ -201,6 +206,7 @@ int build_kparams(gpm_ctx* c, bool init_phase, KParams& P, bool eval_call = fals
     // "quadperm" the samples of a round are dealt to the lanes as 2x2 blocks (x offset i, i+2; y offset j, j+2) where the
     // round contains them, leftovers in window order.  Only WHICH lane evaluates a sample changes; the per-view FMA chain
     // still consumes the dissimilarities in the reference's order.
+    P.prepass = c->opt_prepass;
     P.quadperm = c->opt_quadperm;
     {
         int s0 = 0;
@@ -374,6 +380,7 @@ extern "C" int gpm_create(gpm_ctx** out, int device, int width, int height, int 
     DeviceGuard g(device);
     gpm_ctx* c = new gpm_ctx;
     for (int& v : c->opt_site) v = -1;
+    if (const char* e = getenv("GPM_PREPASS")) c->opt_prepass = atoi(e) != 0;
     c->device = device;  c->W = width;  c->H = height;  c->maxV = max_views;
     c->have_view.assign(max_views, 0);
     c->view_8bit.assign(max_views, 0);
@@ -1371,6 +1378,7 @@ extern "C" int gpm_set_option(gpm_ctx* c, const char* name, int value)
     else if (n == "exchange") c->opt_exchange = value != 0;
     else if (n == "async_upload") c->opt_async_upload = value != 0;
     else if (n == "equal_rounds") c->opt_equal_rounds = value != 0;
+    else if (n == "prepass") c->opt_prepass = value != 0;
     else if (n == "fused_warps") c->opt_fused_warps = value;
     else if (n == "shard_async") c->opt_shard_async = value != 0;
     else return fail(GPM_E_ARG, "gpm_set_option: unknown option '" + n + "'");

@@ -12,6 +12,11 @@ __device__ __forceinline__ unsigned long long* block_mbar(const KParams& P, floa
 {
     return reinterpret_cast<unsigned long long*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 2);
 }
+// list of the tile's pixels that have work to do (k_sweep's pre-pass): 512 x uint16 behind the lane table
+__device__ __forceinline__ unsigned short* block_active(const KParams& P, float* smem_base)
+{
+    return reinterpret_cast<unsigned short*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4 + GPM_MAX_ROUNDS * 8);
+}
 __device__ __forceinline__ unsigned char* block_perm(const KParams& P, float* smem_base)
 {
     return reinterpret_cast<unsigned char*>(smem_base + fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4);
@@ -96,10 +101,10 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, const War
     }
 }
 
-// shared memory: [tile tile_stride*tile_w][cams V*21][pad to 16 B][nwarps * warp_scratch][4 ints: work counter, -, mbarrier (8 B)][lane permutation table, GPM_MAX_ROUNDS x 32 bytes]
+// shared memory: [tile tile_stride*tile_w][cams V*21][pad to 16 B][nwarps * warp_scratch][4 ints: work counter, active count, mbarrier (8 B)][lane permutation table, GPM_MAX_ROUNDS x 32 bytes][active pixel list, 512 x uint16]
 __host__ __device__ inline size_t block_smem_bytes(const KParams& P)
 {
-    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4 + GPM_MAX_ROUNDS * 8;
+    size_t fl = (size_t)fixed_smem_floats(P) + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color) + 4 + GPM_MAX_ROUNDS * 8 + GPM_TILE * GPM_TILE / 4;
     return fl * sizeof(float);
 }
 
@@ -221,19 +226,74 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
     int* counter = reinterpret_cast<int*>(scratch + (size_t)P.nwarps * warp_scratch_floats(P.ns_pad, P.V, P.color));
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_x0 = blockIdx.x * GPM_TILE - P.halo, tile_y0 = blockIdx.y * GPM_TILE - P.halo;
-    if (threadIdx.x == 0) *counter = P.nwarps;
+    if (threadIdx.x == 0) { counter[0] = P.nwarps;  counter[1] = 0; }
     stage_block(P, &tmap, refpad, cams, tile, sCam, tile_x0, tile_y0);
     const WarpScratch ws = carve(scratch + (size_t)warp * warp_scratch_floats(P.ns_pad, P.V, P.color), P.ns_pad, P.V, P.color, block_perm(P, smem));
     const RefCam& cam = P.ref;
     WarpStats st = {0, 0, 0, 0, 0};
     const int W = P.W, H = P.H;
+    constexpr int NC = FUSED ? 20 : 8;
 
     // gridDim.z slices of the tile's 512 pixels of this colour (small images: more, smaller work units -> no idle SMs in
     // the last wave); inside a slice the warps take pixels dynamically
     const int per_slice = (GPM_TILE * GPM_TILE / 2 + (int)gridDim.z - 1) / (int)gridDim.z;
-    const int idx_end = min(GPM_TILE * GPM_TILE / 2, ((int)blockIdx.z + 1) * per_slice);
-    int idx = (int)blockIdx.z * per_slice + (int)warp;
-    while (idx < idx_end) {
+    const int idx_begin = (int)blockIdx.z * per_slice;
+    const int idx_end = min(GPM_TILE * GPM_TILE / 2, idx_begin + per_slice);
+
+    // Pre-pass, one THREAD per pixel: which pixels have anything to do?  A pixel whose every candidate is a memo hit (the
+    // neighbour still carries the identity it was offered before) and whose refinement is known to reject every step needs no
+    // warp at all — the warp path would read its state, skip everything and write the same state back.  In the late
+    // iterations that is most pixels; the warps then only walk the compact list of the others.  (Other exact shortcuts —
+    // history, duplicates, depth range — still run in the warp path: a pixel they would clear is merely listed.)
+    unsigned short* act = block_active(P, smem);
+    if (P.prepass) {
+        unsigned nskip = 0;
+        for (int i = idx_begin + (int)threadIdx.x; i < idx_end; i += (int)blockDim.x) {
+            const int tx = i & 31, ty = i >> 5;
+            const int px = blockIdx.x * GPM_TILE + tx;
+            const int py = blockIdx.y * GPM_TILE + 2 * ty + (((tx & 1) ^ colour) & 1);
+            if (px >= W || py >= H) continue;
+            bool idle = false;
+            unsigned ncand = 0;
+            if (P.memo) {
+                const size_t center = (size_t)py * W + px;
+                const unsigned mmask = M.mask[center];
+                bool all_hit = true;
+                for (int k = 0; k < NC; k++) {
+                    bool ok;
+                    size_t at;
+                    if (FUSED) {
+                        ok = (phase_mask & 1) && px >= kFusedGx0[k] && px <= W - 1 - kFusedGx1[k] && py >= kFusedGy0[k] && py <= H - 1 - kFusedGy1[k];
+                        at = (size_t)(py + kFusedDy[k]) * W + (px + kFusedDx[k]);
+                    } else {
+                        const int dist = k < 4 ? 1 : 5, dir = k & 3;
+                        int qx = px, qy = py;
+                        if (dir == 0)      { ok = py > dist - 1;  qy = py - dist; }
+                        else if (dir == 1) { ok = py < H - dist;  qy = py + dist; }
+                        else if (dir == 2) { ok = px > dist - 1;  qx = px - dist; }
+                        else               { ok = px < W - dist;  qx = px + dist; }
+                        ok = ok && ((phase_mask >> (k >> 2)) & 1);
+                        at = (size_t)qy * W + qx;
+                    }
+                    if (!ok) continue;
+                    ncand++;
+                    if (!((mmask >> k) & 1) || M.seen[center * NC + k] != M.pid[at]) { all_hit = false;  break; }
+                }
+                const bool refine = (phase_mask & 4) != 0;
+                const bool refine_idle = !refine || (P.rng_mode == 0 && (mmask & GPM_MEMO_REFINE) && M.refseen[center] == M.pid[center]);
+                idle = all_hit && refine_idle;
+                if (idle) nskip += ncand + (refine ? 3u : 0u);
+            }
+            if (!idle) act[atomicAdd(&counter[1], 1)] = (unsigned short)i;
+        }
+        nskip = __reduce_add_sync(GPM_FULL, nskip);
+        st.skip += nskip;                       // every lane holds the warp's sum; flush_stats takes lane 0's
+    }
+    __syncthreads();
+    const int nactive = P.prepass ? counter[1] : idx_end - idx_begin;      // without the pre-pass: every pixel of the slice, in order
+    int pos = (int)warp;
+    while (pos < nactive) {
+        const int idx = P.prepass ? (int)act[pos] : idx_begin + pos;
         // pixel of this colour — gipuma.cu:1730-1734 / 1786-1790
         const int tx = idx & 31, ty = idx >> 5;
         const int px = blockIdx.x * GPM_TILE + tx;
@@ -250,7 +310,6 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
 
             // candidate k lives in lane k: 0..3 = up, down, left, right at 1 px (:1571-1582), 4..7 at 5 px (:1450-1462);
             // fused kernel: the 20 candidates of gipuma.cu:1236-1330 in source order
-            constexpr int NC = FUSED ? 20 : 8;
             constexpr unsigned NCMASK = (1u << NC) - 1u;
             float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
             bool mine_ok = false;
@@ -401,8 +460,8 @@ k_sweep(const __grid_constant__ KParams P, const __grid_constant__ CUtensorMap t
                 M.pid[center] = own_id;
             }
         }
-        if (lane == 0) idx = (int)blockIdx.z * per_slice + atomicAdd(counter, 1);
-        idx = __shfl_sync(GPM_FULL, idx, 0);
+        if (lane == 0) pos = atomicAdd(&counter[0], 1);
+        pos = __shfl_sync(GPM_FULL, pos, 0);
     }
     flush_stats(stats, st, lane);
 }

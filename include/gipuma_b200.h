@@ -191,6 +191,8 @@ int gpm_debug_packed_mismatches(gpm_ctx* ctx, unsigned* count, float* records512
  * "exchange" (1): view shard over peer memory when regions are attached, 0 = NCCL all-gather per stage;
  * "async_upload" (0): 1 lets gpm_set_reference / gpm_set_view return without a host synchronisation — the caller keeps its
  * (page-locked) image buffers unchanged until the next gpm_run / gpm_sweep returns;
+ * "prepass" (0; environment GPM_PREPASS=1 at gpm_create): a thread-per-pixel pre-pass of the sweep kernel lists the pixels
+ * that still have work, so that converged pixels cost no warp;
  * "quadperm" (1): deal the samples of a round to the lanes as 2x2 blocks per hardware quad (texture-unit locality);
  * "neighbours" (8): 20 selects the reference's fused sweep — the kernels it launches when built without SMALLKERNEL
  * (gipuma.cu:1122-1351, 1913-1940): 12 axial + 8 knight-move neighbours, then refinement, one launch per colour; bit-exact
