@@ -111,3 +111,31 @@ def test_view_shard_merge_world2_gloo(tmp_path, n_views, n_best):
         assert ok == "1" and same == "1" and float(tmax) == 11.0
         seen += [int(x) for x in refs.split(",") if x]
     assert sorted(seen) == list(range(5))
+
+
+def test_bench_sharded_layout_covers_every_view_once():
+    """bench.py's view_shard / hybrid modes: every group's ranks together hold each source view exactly once, rank 0 is the one
+    that also runs the unsharded comparison, and `--shard` must divide the world size."""
+    import argparse
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module2", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for world, mode, shard_opt, config, nviews in ((2, "auto", 0, 6, 60), (8, "auto", 0, 6, 60), (4, "view_shard", 0, 4, 47), (8, "hybrid", 4, 5, 64), (4, "hybrid", 0, 5, 64)):
+        args = argparse.Namespace(mode=mode, config=config if mode != "auto" else 0, shard=shard_opt, color=False, neighbours=8, scene="smooth", no_check=False)
+        m, cfg, shard = bench.resolve(args, world)
+        assert cfg == config and world % shard == 0
+        per_group = {}
+        checks = 0
+        for rank in range(world):
+            group, rank_in, members, mine, check = bench.sharded_layout(args, cfg, shard, rank, world)
+            per_group.setdefault(group, []).extend(mine)
+            checks += int(check)
+            assert rank in members[group] and members[group][rank_in] == rank
+        assert checks == 1
+        assert len(per_group) == world // shard
+        for views in per_group.values():
+            assert sorted(views) == list(range(nviews))
+    with pytest.raises(SystemExit):
+        bench.resolve(argparse.Namespace(mode="hybrid", config=0, shard=3, color=False, neighbours=8, scene="smooth"), 8)
