@@ -72,8 +72,20 @@ def build_dropin(force: bool = False):
     return out
 
 
+def build_examples(force: bool = False):
+    """examples/shard_host: the C++ multi-GPU host over the C-ABI (plain g++, no CUDA headers)."""
+    src = os.path.join(ROOT, "examples", "shard_host.cpp")
+    out = os.path.join(ROOT, "examples", "shard_host")
+    lib = build_library()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(lib)):
+        return out
+    _run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-L" + HERE, "-lgipuma_b200", "-lpthread",
+          "-Wl,-rpath,$ORIGIN/../gipuma_b200", "-o", out])
+    return out
+
+
 def build_all(force: bool = False):
-    outs = [build_library(force)]
+    outs = [build_library(force), build_examples(force)]
     d = build_dropin(force)
     if d:
         outs.append(d)
