@@ -112,3 +112,26 @@ def test_bench_arms_describe_the_same_workload():
             assert m == "single" and cfg == 2
         if mode == "auto" and world > 1:
             assert m == "view_shard" and cfg == 6 and shard == world
+
+
+def test_batch_driver_validates_arguments_and_has_no_cpu_fallback():
+    """gpm_batch_run (host C++): bad descriptors are refused before any CUDA call; without a device the workers fail loudly
+    (no CPU path), with the reason in gpm_batch_last_error()."""
+    import numpy as np
+    from gipuma_b200 import api, scene as S
+    params = S.AlgorithmParameters(box_hsize=9, box_vsize=9, iterations=1, n_best=2, cost_comb=S.COMB_BEST_N)
+    params.depthMin, params.depthMax = 300.0, 800.0
+    P = [S.load_dtu_projections()[i] for i in range(3)]
+    imgs = np.zeros((3, 64, 96), np.float32)
+    with pytest.raises(api.GipumaError, match="bad arguments"):
+        api.batch_run(imgs[:1], P[:1], params, [0])                       # a reference view needs at least one source view
+    with pytest.raises(api.GipumaError, match="bad arguments"):
+        api.batch_run(imgs, P, params, [0], max_views=0)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:      # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(api.GipumaError, match="CUDA"):
+            api.batch_run(imgs, P, params, [0], cam_scale=1600.0 / 96)
