@@ -135,3 +135,24 @@ def test_batch_driver_validates_arguments_and_has_no_cpu_fallback():
     if not has_gpu:
         with pytest.raises(api.GipumaError, match="CUDA"):
             api.batch_run(imgs, P, params, [0], cam_scale=1600.0 / 96)
+
+
+def test_cpp_host_example_builds_and_fails_loudly_without_a_device(tmp_path):
+    """examples/shard_host.cpp links against the C-ABI with plain g++ (no CUDA headers); without a GPU it must exit non-zero
+    with the library's "no CUDA device" message — there is no CPU path to fall back to."""
+    from gipuma_b200 import build, scene as S
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import dump_scene
+    exe = build.build_examples()
+    assert os.path.exists(exe)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: covered by tests/test_gpu_cpp_host.py")
+    except ImportError:
+        pass
+    sc = S.make_config(1, rows=64, cols=96)
+    scene_file = str(tmp_path / "scene.bin")
+    dump_scene.dump(sc, scene_file)
+    p = subprocess.run([exe, scene_file, str(tmp_path / "out.bin"), "1"], capture_output=True, text=True, timeout=120)
+    assert p.returncode != 0 and "CUDA" in p.stderr
